@@ -1,0 +1,562 @@
+// C ABI of cbfssm_b200 (see include/cbfssm_b200.h): shape checks, workspace layout,
+// chain schedule, kernel dispatch and the small float64 reduction kernels.
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+#include "common.cuh"
+#include "dims_list.h"
+
+namespace cbf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define CBF_DECLARE_OPS(DX, DU, DY) const DimOps *ops_##DX##_##DU##_##DY();
+CBF_DIMS_LIST(CBF_DECLARE_OPS)
+#undef CBF_DECLARE_OPS
+
+const DimOps *find_ops(int dx, int du, int dy) {
+#define CBF_MATCH_OPS(DX, DU, DY) \
+  if (dx == DX && du == DU && dy == DY) return ops_##DX##_##DU##_##DY();
+  CBF_DIMS_LIST(CBF_MATCH_OPS)
+#undef CBF_MATCH_OPS
+  return nullptr;
+}
+
+constexpr int kMaxGridRev = 148 * 8;   // upper bound on persistent reverse CTAs (workspace sizing)
+constexpr size_t kMaxSmem = 227 * 1024;
+
+// Live chain segments of both backward-message runs (cbfssm.py:123-136, SURVEY 8a note 5).
+static std::vector<Chain> build_chains(int T, int R) {
+  std::vector<Chain> out;
+  for (int run = 0; run < 2; ++run) {
+    const int off = run == 0 ? 1 : R + 1;
+    std::vector<int> starts;
+    starts.push_back(T - 1);
+    for (int t = T - 2; t >= 0; --t)
+      if ((t + off) % (2 * R) == 0) starts.push_back(t);
+    for (size_t i = 0; i < starts.size(); ++i) {
+      const int t_hi = starts[i];
+      const int t_next = (i + 1 < starts.size()) ? starts[i + 1] : -1;
+      const bool resample = (t_hi + off) % (2 * R) == 0;
+      int t_lo = -1;
+      for (int t = t_hi; t > t_next; --t)
+        if (writer_run(t, R) == run) t_lo = t;
+      if (t_lo < 0) continue;   // segment writes nothing: dead work
+      out.push_back(Chain{run, t_hi, t_lo, resample ? 1 : 0});
+    }
+  }
+  return out;
+}
+
+struct Plan {
+  Dims D;
+  int dx, du, dy, dh, din;
+  int ptiles;
+  std::vector<Chain> chains;
+  AccLayout Lf, Lb;
+  size_t off_X, off_H, off_Yb, off_fbm, off_ffw, off_gf, off_gb, off_accf, off_accb, off_stats, total;
+  const DimOps *ops;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
+  if (!s) { set_error("shape is NULL"); return CBF_ERR_NULL; }
+  if (s->B < 1 || s->S < 1 || s->T < 1 || s->M < 1 || s->dx < 2 || s->du < 0 || s->dy < 1 || s->dy >= s->dx ||
+      s->R < 1 || s->n_local < 1 || s->n_offset < 0 || (int64_t)s->n_offset + s->n_local > (int64_t)s->B * s->S) {
+    set_error("invalid shape B=%d S=%d T=%d M=%d dx=%d du=%d dy=%d R=%d n_offset=%d n_local=%d", s->B, s->S, s->T,
+              s->M, s->dx, s->du, s->dy, s->R, s->n_offset, s->n_local);
+    return CBF_ERR_INVALID_SHAPE;
+  }
+  p.dx = s->dx; p.du = s->du; p.dy = s->dy; p.dh = s->dx - s->dy; p.din = s->dx + s->du;
+  p.ops = find_ops(s->dx, s->du, s->dy);
+  if (need_ops && !p.ops) {
+    set_error("dims (dx=%d,du=%d,dy=%d) are not compiled in (see csrc/dims_list.h)", s->dx, s->du, s->dy);
+    return CBF_ERR_UNSUPPORTED_DIMS;
+  }
+  if (p.ops) {
+    for (int w = 0; w < 4; ++w)
+      if (p.ops->smem_bytes(s->M, w) > kMaxSmem) {
+        set_error("M=%d: resident parameter set needs %zu B of shared memory (> %zu)", s->M,
+                  p.ops->smem_bytes(s->M, w), kMaxSmem);
+        return CBF_ERR_UNSUPPORTED_M;
+      }
+  }
+  Dims &D = p.D;
+  D.B = s->B; D.S = s->S; D.T = s->T; D.M = s->M; D.R = s->R; D.condition = s->condition ? 1 : 0;
+  D.n_offset = s->n_offset; D.n_local = s->n_local; D.kap = s->k_factor;
+  D.npad = round_up(s->n_local, 32);
+  p.ptiles = ceil_div(s->n_local, kNP);
+  p.chains = build_chains(s->T, s->R);
+  p.Lf = AccLayout(s->M, p.din, p.dx, p.dx);
+  p.Lb = AccLayout(s->M, p.din, p.dh, p.dx);
+  size_t o = 0;
+  const size_t np = D.npad;
+  p.off_X = o; o = align_up(o + sizeof(float) * s->T * p.dx * np, 256);
+  p.off_H = o; o = align_up(o + sizeof(float) * 2 * s->T * p.dh * np, 256);
+  p.off_Yb = o; o = align_up(o + sizeof(float) * s->T * p.dh * np, 256);
+  p.off_fbm = o; o = align_up(o + sizeof(float) * p.chains.size() * p.ptiles, 256);
+  p.off_ffw = o; o = align_up(o + sizeof(float) * p.ptiles * (p.dy + 1), 256);
+  p.off_gf = o; o = align_up(o + sizeof(float) * (size_t)kMaxGridRev * p.Lf.slot(), 256);
+  p.off_gb = o; o = align_up(o + sizeof(float) * (size_t)kMaxGridRev * p.Lb.slot(), 256);
+  p.off_accf = o; o = align_up(o + sizeof(double) * p.Lf.slot(), 256);
+  p.off_accb = o; o = align_up(o + sizeof(double) * p.Lb.slot(), 256);
+  p.off_stats = o; o = align_up(o + sizeof(double) * (p.dy + 2), 256);
+  p.total = o;
+  return 0;
+}
+
+static Workspace bind_workspace(const Plan &p, void *base) {
+  char *b = static_cast<char *>(base);
+  Workspace w;
+  w.X = reinterpret_cast<float *>(b + p.off_X);
+  w.H = reinterpret_cast<float *>(b + p.off_H);
+  w.Yb = reinterpret_cast<float *>(b + p.off_Yb);
+  w.fpart_bm = reinterpret_cast<float *>(b + p.off_fbm);
+  w.fpart_fw = reinterpret_cast<float *>(b + p.off_ffw);
+  w.gpart_f = reinterpret_cast<float *>(b + p.off_gf);
+  w.gpart_b = reinterpret_cast<float *>(b + p.off_gb);
+  w.acc_f = reinterpret_cast<double *>(b + p.off_accf);
+  w.acc_b = reinterpret_cast<double *>(b + p.off_accb);
+  w.stats = reinterpret_cast<double *>(b + p.off_stats);
+  w.npad = p.D.npad;
+  return w;
+}
+
+static cbf_grad_layout grad_layout(const Plan &p) {
+  cbf_grad_layout g;
+  const int64_t M = p.D.M;
+  int64_t o = 0;
+  g.f_P = o; o += M * M;
+  g.f_alpha = o; o += M * p.dx;
+  g.f_S = o; o += M * p.dx;
+  g.f_Z = o; o += M * p.din;
+  g.f_ell = o; o += p.din;
+  g.f_sig2 = o; o += 1;
+  g.b_P = o; o += M * M;
+  g.b_alpha = o; o += M * p.dh;
+  g.b_S = o; o += M * p.dh;
+  g.b_Z = o; o += M * p.din;
+  g.b_ell = o; o += p.din;
+  g.b_sig2 = o; o += 1;
+  g.var_x = o; o += p.dx;
+  g.var_y = o; o += p.dx;
+  g.total = o;
+  return g;
+}
+
+static bool misaligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+
+// ------------------------------------------------------------------------------------
+// small float64 kernels
+// ------------------------------------------------------------------------------------
+// terms[0] = loglik (cbfssm.py:245-251), terms[1] = kl_x (:183), terms[2] = entropy (:99)
+__global__ void finalize_terms_kernel(const float *__restrict__ fbm, int nbm, const float *__restrict__ ffw,
+                                      int ptiles, int dy, const float *__restrict__ vy, double n_times_t,
+                                      double *__restrict__ stats, double *__restrict__ terms) {
+  __shared__ double sh[256];
+  const int tid = threadIdx.x;
+  for (int q = 0; q < dy + 2; ++q) {
+    double s = 0.0;
+    if (q <= dy) {
+      for (int i = tid; i < ptiles; i += blockDim.x) s += (double)ffw[(size_t)i * (dy + 1) + q];
+    } else {
+      for (int i = tid; i < nbm; i += blockDim.x) s += (double)fbm[i];
+    }
+    sh[tid] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if (tid < o) sh[tid] += sh[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0) stats[q] = sh[0];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double ll = 0.0;
+    for (int j = 0; j < dy; ++j) {
+      const double v = (double)vy[j];
+      ll += -0.5 * stats[j] / v - 0.5 * n_times_t * (log(v) + 1.8378770664093454836);
+    }
+    terms[0] = ll;
+    terms[1] = stats[dy];
+    terms[2] = stats[dy + 1];
+  }
+}
+
+__global__ void reduce_slots_kernel(const float *__restrict__ part, int nslots, int slot, double *__restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= slot) return;
+  double s = 0.0;
+  for (int i = 0; i < nslots; ++i) s += (double)part[(size_t)i * slot + e];
+  out[e] = s;
+}
+
+// Decode one GP's reduced accumulators into the flat kernel-level gradient.
+__global__ void finalize_gp_grad_kernel(AccLayout L, const double *__restrict__ acc, GpDev gp,
+                                        double *__restrict__ gP, double *__restrict__ galpha,
+                                        double *__restrict__ gS, double *__restrict__ gZ,
+                                        double *__restrict__ gell, double *__restrict__ gsig2) {
+  const int M = L.M, MG = L.MG, DG = L.DG, CG = L.CG, Din = L.Din, Dout = L.Dout;
+  auto at = [&](int m, int col) -> double {
+    const int rg = m >> 2, r = m & 3, cg = col >> 2, c = col & 3;
+    return acc[((size_t)r * L.ntiles + (rg * CG + cg)) * 4 + c];
+  };
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = tid; i < M * M; i += nt) gP[i] = at(i / M, i % M);
+  for (int i = tid; i < M * Dout; i += nt) {
+    const int m = i / Dout, d = i % Dout;
+    galpha[i] = at(m, 4 * MG + d);
+    gS[i] = at(m, 4 * (MG + DG) + d);
+  }
+  const int xc = 4 * (MG + 2 * DG);
+  for (int i = tid; i < M * Din; i += nt) {
+    const int m = i / Din, j = i % Din;
+    const double ell = (double)gp.ell[j];
+    const double zt = (double)gp.Z[i] / ell;
+    gZ[i] = (at(m, xc + j) - zt * at(m, xc + Din)) / ell;
+  }
+  const double *sc = acc + L.nacc;
+  for (int j = tid; j < Din; j += nt) gell[j] = sc[j] / (double)gp.ell[j];
+  if (tid == 0) gsig2[0] = sc[Din] / (double)gp.sig2[0] + sc[Din + 1];
+}
+
+__global__ void finalize_noise_grad_kernel(int dx, int dy, int Din, const double *__restrict__ sc_f,
+                                           const double *__restrict__ sc_b, const double *__restrict__ stats,
+                                           const float *__restrict__ vy, double w_ll, double n_times_t,
+                                           double *__restrict__ gvx, double *__restrict__ gvy) {
+  const int j = threadIdx.x;
+  if (j >= dx) return;
+  gvx[j] = sc_f[Din + 2 + j] + sc_b[Din + 2 + j];
+  double g = sc_f[Din + 2 + dx + j];
+  if (j < dy) {
+    const double v = (double)vy[j];
+    g += w_ll * (0.5 * stats[j] / (v * v) - 0.5 * n_times_t / v);
+  }
+  gvy[j] = g;
+}
+
+// x_final / y_tilde in the reference layout [nb, T, S, dx]  (cbfssm.py:97,181)
+__global__ void export_states_kernel(Dims D, int dx, int dy, const float *__restrict__ y, Workspace ws,
+                                     float *__restrict__ x_final, float *__restrict__ y_tilde) {
+  const int dh = dx - dy;
+  const size_t total = (size_t)D.n_local * D.T * dx;
+  const size_t np = ws.npad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % dx);
+    size_t r = i / dx;
+    const int s = (int)(r % D.S); r /= D.S;
+    const int t = (int)(r % D.T);
+    const int bl = (int)(r / D.T);
+    const int nl = bl * D.S + s;
+    if (x_final) x_final[i] = ws.X[((size_t)t * dx + j) * np + nl];
+    if (y_tilde) {
+      float v;
+      if (j < dy) {
+        const int b = (D.n_offset + nl) / D.S;
+        v = y[((size_t)b * D.T + t) * dy + j];
+      } else {
+        v = ws.H[(((size_t)writer_run(t, D.R) * D.T + t) * dh + (j - dy)) * np + nl];
+      }
+      y_tilde[i] = v;
+    }
+  }
+}
+
+// tf.nn.moments(axes=[2]) over the particle axis (cbfssm.py:267-269): one warp per (b,t).
+__global__ void moments_kernel(const float *__restrict__ x, int rows, int S, int d, int d_keep,
+                               const float *__restrict__ add_var, float *__restrict__ mean,
+                               float *__restrict__ var) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  for (int j = 0; j < d_keep; ++j) {
+    double s1 = 0.0;
+    for (int s = lane; s < S; s += 32) s1 += (double)x[((size_t)warp * S + s) * d + j];
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    const double mu = s1 / S;
+    double s2 = 0.0;
+    for (int s = lane; s < S; s += 32) {
+      const double e = (double)x[((size_t)warp * S + s) * d + j] - mu;
+      s2 += e * e;
+    }
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == 0) {
+      mean[(size_t)warp * d_keep + j] = (float)mu;
+      var[(size_t)warp * d_keep + j] = (float)(s2 / S + (add_var ? (double)add_var[j] : 0.0));
+    }
+  }
+}
+
+__global__ void adam_kernel(int64_t n, double *__restrict__ theta, const double *__restrict__ grad,
+                            double *__restrict__ m, double *__restrict__ v, double lr_t, double b1, double b2,
+                            double eps) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double g = grad[i];
+  const double mi = b1 * m[i] + (1.0 - b1) * g;
+  const double vi = b2 * v[i] + (1.0 - b2) * g * g;
+  m[i] = mi;
+  v[i] = vi;
+  theta[i] -= lr_t * mi / (sqrt(vi) + eps);
+}
+
+// Philox4x32-10 (Salmon et al. 2011) -> Box-Muller; counter = element index / 4.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__global__ void fill_normal_kernel(float *__restrict__ out, int64_t n, uint64_t seed, uint64_t stream_id) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  float z[4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
+    const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;
+    const float rr = sqrtf(-2.f * logf(u1));
+    float sn, cs;
+    sincospif(2.f * u2, &sn, &cs);
+    z[2 * h] = rr * cs;
+    z[2 * h + 1] = rr * sn;
+  }
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+    if (q * 4 + h < n) out[q * 4 + h] = z[h];
+}
+
+static int device_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+static int rev_grid(const Plan &p, int which, int items) {
+  int occ = p.ops->occupancy(p.D.M, which);
+  if (occ < 1) occ = 1;
+  int g = device_sms() * occ;
+  if (g > kMaxGridRev) g = kMaxGridRev;
+  if (g > items) g = items;
+  return g < 1 ? 1 : g;
+}
+
+static GpDev to_dev(const cbf_gp *g) { return GpDev{g->Z, g->ell, g->sig2, g->P, g->alpha, g->S}; }
+
+static int check_gp(const cbf_gp *g, const char *name) {
+  if (!g || !g->Z || !g->ell || !g->sig2 || !g->P || !g->alpha || !g->S) {
+    set_error("%s has a NULL operand", name);
+    return CBF_ERR_NULL;
+  }
+  if (misaligned(g->Z) || misaligned(g->P) || misaligned(g->alpha) || misaligned(g->S)) {
+    set_error("%s operands must be 16-byte aligned", name);
+    return CBF_ERR_ALIGNMENT;
+  }
+  return 0;
+}
+
+#define CBF_CUDA(expr)                                                         \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(_e));               \
+      return (int)_e;                                                          \
+    }                                                                          \
+  } while (0)
+
+}  // namespace cbf
+
+using namespace cbf;
+
+extern "C" {
+
+CBF_API int cbf_abi_version(void) { return CBF_ABI_VERSION; }
+
+CBF_API const char *cbf_last_error_string(void) { return g_err; }
+
+CBF_API int cbf_supported(int32_t M, int32_t dx, int32_t du, int32_t dy) {
+  const DimOps *ops = find_ops(dx, du, dy);
+  if (!ops || M < 1) return 0;
+  for (int w = 0; w < 4; ++w)
+    if (ops->smem_bytes(M, w) > kMaxSmem) return 0;
+  return 1;
+}
+
+CBF_API int cbf_workspace_bytes(const cbf_shape *shape, size_t *bytes_out) {
+  if (!bytes_out) { set_error("bytes_out is NULL"); return CBF_ERR_NULL; }
+  Plan p;
+  int rc = make_plan(shape, p, false);
+  if (rc) return rc;
+  *bytes_out = p.total;
+  return 0;
+}
+
+CBF_API int cbf_grad_layout_get(const cbf_shape *shape, cbf_grad_layout *out) {
+  if (!out) { set_error("out is NULL"); return CBF_ERR_NULL; }
+  Plan p;
+  int rc = make_plan(shape, p, false);
+  if (rc) return rc;
+  *out = grad_layout(p);
+  return 0;
+}
+
+CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
+                     const float *var_y, const float *u, const float *y, const float *eps_b, const float *z_b,
+                     const float *eps_f, double *terms, void *workspace, void *stream) {
+  Plan p;
+  int rc = make_plan(shape, p, true);
+  if (rc) return rc;
+  if ((rc = check_gp(gp_f, "gp_f")) || (rc = check_gp(gp_b, "gp_b"))) return rc;
+  if (!var_x || !var_y || !u || !y || !eps_b || !z_b || (!eps_f && shape->T > 1) || !terms || !workspace) {
+    set_error("cbf_elbo_forward: NULL argument");
+    return CBF_ERR_NULL;
+  }
+  if (misaligned(workspace)) { set_error("workspace must be 16-byte aligned"); return CBF_ERR_ALIGNMENT; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws = bind_workspace(p, workspace);
+  const int nch = (int)p.chains.size();
+  for (int c0 = 0; c0 < nch; c0 += kMaxChains) {
+    ChainTable ct;
+    ct.count = nch - c0 < kMaxChains ? nch - c0 : kMaxChains;
+    memcpy(ct.c, p.chains.data() + c0, sizeof(Chain) * ct.count);
+    CBF_CUDA(p.ops->bm_forward(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, ws,
+                               ws.fpart_bm + (size_t)c0 * p.ptiles, st));
+  }
+  CBF_CUDA(p.ops->fw_forward(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, ws, ws.fpart_fw, st));
+  finalize_terms_kernel<<<1, 256, 0, st>>>(ws.fpart_bm, nch * p.ptiles, ws.fpart_fw, p.ptiles, p.dy, var_y,
+                                           (double)p.D.n_local * p.D.T, ws.stats, terms);
+  CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
+                      const float *var_y, const float *u, const float *y, const float *eps_b, const float *z_b,
+                      const float *eps_f, const double *term_weights_host, double *grad_flat, void *workspace,
+                      void *stream) {
+  Plan p;
+  int rc = make_plan(shape, p, true);
+  if (rc) return rc;
+  if ((rc = check_gp(gp_f, "gp_f")) || (rc = check_gp(gp_b, "gp_b"))) return rc;
+  if (!var_x || !var_y || !u || !y || !eps_b || !z_b || (!eps_f && shape->T > 1) || !term_weights_host ||
+      !grad_flat || !workspace) {
+    set_error("cbf_elbo_backward: NULL argument");
+    return CBF_ERR_NULL;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws = bind_workspace(p, workspace);
+  const cbf_grad_layout gl = grad_layout(p);
+  const float w_ll = (float)term_weights_host[0], w_kl = (float)term_weights_host[1],
+              w_en = (float)term_weights_host[2];
+
+  // reverse of the forward rollout (writes the y2 adjoints), then of the message chains
+  const int grid_f = rev_grid(p, 2, p.ptiles);
+  CBF_CUDA(p.ops->fw_reverse(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, ws.gpart_f, grid_f, st));
+  reduce_slots_kernel<<<ceil_div(p.Lf.slot(), 256), 256, 0, st>>>(ws.gpart_f, grid_f, p.Lf.slot(), ws.acc_f);
+  CBF_CUDA(cudaGetLastError());
+
+  const int nch = (int)p.chains.size();
+  int nslots_b = 0;
+  for (int c0 = 0; c0 < nch; c0 += kMaxChains) {
+    ChainTable ct;
+    ct.count = nch - c0 < kMaxChains ? nch - c0 : kMaxChains;
+    memcpy(ct.c, p.chains.data() + c0, sizeof(Chain) * ct.count);
+    int grid_b = rev_grid(p, 3, p.ptiles * ct.count);
+    if (nslots_b + grid_b > kMaxGridRev) grid_b = kMaxGridRev - nslots_b;
+    if (grid_b < 1) { set_error("too many chain batches"); return CBF_ERR_INVALID_SHAPE; }
+    CBF_CUDA(p.ops->bm_reverse(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, w_en, ws,
+                               ws.gpart_b + (size_t)nslots_b * p.Lb.slot(), grid_b, st));
+    nslots_b += grid_b;
+  }
+  reduce_slots_kernel<<<ceil_div(p.Lb.slot(), 256), 256, 0, st>>>(ws.gpart_b, nslots_b, p.Lb.slot(), ws.acc_b);
+  CBF_CUDA(cudaGetLastError());
+
+  finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lf, ws.acc_f, to_dev(gp_f), grad_flat + gl.f_P, grad_flat + gl.f_alpha,
+                                             grad_flat + gl.f_S, grad_flat + gl.f_Z, grad_flat + gl.f_ell,
+                                             grad_flat + gl.f_sig2);
+  finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lb, ws.acc_b, to_dev(gp_b), grad_flat + gl.b_P, grad_flat + gl.b_alpha,
+                                             grad_flat + gl.b_S, grad_flat + gl.b_Z, grad_flat + gl.b_ell,
+                                             grad_flat + gl.b_sig2);
+  finalize_noise_grad_kernel<<<1, 32 * ceil_div(p.dx, 32), 0, st>>>(
+      p.dx, p.dy, p.din, ws.acc_f + p.Lf.nacc, ws.acc_b + p.Lb.nacc, ws.stats, var_y, (double)term_weights_host[0],
+      (double)p.D.n_local * p.D.T, grad_flat + gl.var_x, grad_flat + gl.var_y);
+  CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+CBF_API int cbf_export_states(const cbf_shape *shape, const float *y, float *x_final, float *y_tilde,
+                      const void *workspace, void *stream) {
+  Plan p;
+  int rc = make_plan(shape, p, false);
+  if (rc) return rc;
+  if (!workspace || !y) { set_error("cbf_export_states: NULL argument"); return CBF_ERR_NULL; }
+  if (shape->n_local % shape->S != 0 || shape->n_offset % shape->S != 0) {
+    set_error("cbf_export_states needs a sequence-aligned shard (n_offset, n_local multiples of S)");
+    return CBF_ERR_INVALID_SHAPE;
+  }
+  Workspace ws = bind_workspace(p, const_cast<void *>(workspace));
+  const size_t total = (size_t)p.D.n_local * p.D.T * p.dx;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  export_states_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p.D, p.dx, p.dy, y, ws, x_final, y_tilde);
+  CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+CBF_API int cbf_moments(const float *x, int32_t nb, int32_t T, int32_t S, int32_t d, int32_t d_keep, const float *add_var,
+                float *mean, float *var, void *stream) {
+  if (!x || !mean || !var) { set_error("cbf_moments: NULL argument"); return CBF_ERR_NULL; }
+  if (nb < 1 || T < 1 || S < 1 || d < 1 || d_keep < 1 || d_keep > d) {
+    set_error("cbf_moments: invalid shape");
+    return CBF_ERR_INVALID_SHAPE;
+  }
+  const int rows = nb * T;
+  moments_kernel<<<ceil_div(rows * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, S, d, d_keep,
+                                                                                         add_var, mean, var);
+  CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+CBF_API int cbf_adam_step(int64_t n, double *theta, const double *grad, double *m, double *v, int64_t step, double lr,
+                  double beta1, double beta2, double eps, void *stream) {
+  if (!theta || !grad || !m || !v) { set_error("cbf_adam_step: NULL argument"); return CBF_ERR_NULL; }
+  if (n < 1 || step < 1) { set_error("cbf_adam_step: invalid n/step"); return CBF_ERR_INVALID_SHAPE; }
+  const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, theta, grad, m, v, lr_t,
+                                                                                         beta1, beta2, eps);
+  CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+CBF_API int cbf_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t stream_id, void *stream) {
+  if (!out) { set_error("cbf_fill_normal: NULL argument"); return CBF_ERR_NULL; }
+  if (n < 1) return 0;
+  const int64_t quads = (n + 3) / 4;
+  fill_normal_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed,
+                                                                                                    stream_id);
+  CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Shared declarations of the cbfssm_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/cbfssm_b200.h"
+
+namespace cbf {
+
+constexpr int kNP = 32;          // particles per CTA tile in the cooperative (generic) path
+constexpr int kLD = kNP + 4;     // row stride of the [m][n] shared arrays (== 4 mod 32: conflict-free float4 rows)
+constexpr int kMaxChains = 120;  // chain segments per launch (kernel parameter space)
+constexpr float kLog2PiE = 2.8378770664093453f;   // log(2*pi*e)
+constexpr float kNegHalfLog2e = -0.72134752044448170f;  // -0.5 * log2(e)
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// One live segment of a backward-message run (cbfssm.py:123-136): steps t = t_hi .. t_lo.
+struct Chain {
+  int run;
+  int t_hi;
+  int t_lo;
+  int init;  // 0: h = 0 (cbfssm.py:106)   1: h = tile(z_b[run, t_hi]) (cbfssm.py:133-135)
+};
+struct ChainTable {
+  int count;
+  Chain c[kMaxChains];
+};
+
+struct GpDev {
+  const float *Z, *ell, *sig2, *P, *alpha, *S;
+};
+
+// Device views into the caller's workspace.
+struct Workspace {
+  float *X;        // [T][dx][npad]      forward states x_t                      (cbfssm.py:166-169,229)
+  float *H;        // [2][T][dh][npad]   backward-message outputs of both runs   (cbfssm.py:150,158)
+  float *Yb;       // [T][dh][npad]      adjoint of y2[t]
+  float *fpart_bm; // [nchains][ptiles]  entropy partial per CTA
+  float *fpart_fw; // [ptiles][dy+1]     sse_j, kl_x partial per CTA
+  float *gpart_f;  // [grid][slot_f]     reverse partials, forward-rollout GP
+  float *gpart_b;  // [grid][slot_b]     reverse partials, backward-message GP
+  double *acc_f;   // [slot_f]           reduced
+  double *acc_b;   // [slot_b]
+  double *stats;   // sse[dy], kl_x, entropy of this shard (float64)
+  int npad;
+};
+
+// Per-problem constants derived from cbf_shape for the kernels.
+struct Dims {
+  int B, S, T, M, R, condition, n_offset, n_local, npad;
+  float kap;
+};
+
+inline __host__ __device__ int writer_run(int t, int R) { return (t % (2 * R)) < R ? 0 : 1; }
+
+// Layout of one reverse-pass accumulator block for a GP with (M, Din, Dout):
+// tiles of 4x4 outputs, index = (r * ntiles + tile) * 4 + c, tile = rg * CG + cg.
+struct AccLayout {
+  int M, MP, MG, Din, Dout, DG, XG, CG, ntiles, nacc;  // nacc = ntiles*16
+  int nscal;                                           // per-CTA scalar sums appended after the tiles
+  __host__ __device__ AccLayout() {}
+  __host__ __device__ AccLayout(int M_, int Din_, int Dout_, int dx) {
+    M = M_; Din = Din_; Dout = Dout_;
+    MP = round_up(M, 4); MG = MP / 4;
+    DG = ceil_div(Dout, 4); XG = ceil_div(Din + 1, 4);
+    CG = MG + 2 * DG + XG;
+    ntiles = MG * CG; nacc = ntiles * 16;
+    nscal = Din + 2 + 2 * dx;   // L_j[Din], sum w, sum G, var_x_bar[dx], var_y_bar[dx]
+  }
+  __host__ __device__ int slot() const { return nacc + round_up(nscal, 4); }
+};
+
+// Kernel entry points of one (dx,du,dy) instantiation, filled by CBF_INSTANTIATE.
+struct DimOps {
+  int dx, du, dy;
+  cudaError_t (*bm_forward)(const Dims &, const ChainTable &, GpDev, const float *vx, const float *u,
+                            const float *y, const float *eps_b, const float *z_b, Workspace, float *part_out,
+                            cudaStream_t);
+  cudaError_t (*fw_forward)(const Dims &, GpDev, const float *vx, const float *vy, const float *u,
+                            const float *y, const float *eps_f, Workspace, float *part_out, cudaStream_t);
+  cudaError_t (*fw_reverse)(const Dims &, GpDev, const float *vx, const float *vy, const float *u,
+                            const float *y, const float *eps_f, float w_ll, float w_kl, Workspace,
+                            float *part_out, int grid, cudaStream_t);
+  cudaError_t (*bm_reverse)(const Dims &, const ChainTable &, GpDev, const float *vx, const float *u,
+                            const float *y, const float *eps_b, const float *z_b, float w_en, Workspace,
+                            float *part_out, int grid, cudaStream_t);
+  size_t (*smem_bytes)(int M, int which);  // which: 0 bm_fwd 1 fw_fwd 2 fw_rev 3 bm_rev
+  int (*occupancy)(int M, int which);      // resident CTAs/SM of the persistent reverse kernels
+};
+
+const DimOps *find_ops(int dx, int du, int dy);
+
+void set_error(const char *fmt, ...);
+
+}  // namespace cbf
