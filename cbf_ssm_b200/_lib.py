@@ -60,6 +60,8 @@ _SIGNATURES = {
     "cbf_adam_step": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, _P]),
     "cbf_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
+    "cbf_timing_enable": (C.c_int, [C.c_int]),
+    "cbf_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -30,6 +30,34 @@ const DimOps *find_ops(int dx, int du, int dy) {
   return nullptr;
 }
 
+// ---- optional per-kernel device timing (bench.py roofline): thread-local, off by default ----
+struct TimingPool {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;      // pairs (start, stop)
+  std::vector<int> kind;            // 0 bm_forward 1 fw_forward 2 fw_reverse 3 bm_reverse
+  size_t used = 0;
+};
+static thread_local TimingPool g_timing;
+
+struct ScopedTiming {
+  cudaStream_t st;
+  bool on;
+  size_t idx;
+  ScopedTiming(int kind, cudaStream_t s) : st(s), on(g_timing.enabled), idx(0) {
+    if (!on) return;
+    TimingPool &t = g_timing;
+    if (t.used * 2 >= t.ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+      t.ev.push_back(a); t.ev.push_back(b); t.kind.push_back(kind);
+    }
+    idx = t.used++;
+    t.kind[idx] = kind;
+    cudaEventRecord(t.ev[2 * idx], st);
+  }
+  ~ScopedTiming() { if (on) cudaEventRecord(g_timing.ev[2 * idx + 1], st); }
+};
+
 constexpr int kMaxGridRev = 148 * 8;   // upper bound on persistent reverse CTAs (workspace sizing)
 constexpr size_t kMaxSmem = 227 * 1024;
 
@@ -441,10 +469,14 @@ CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const c
     ChainTable ct;
     ct.count = nch - c0 < kMaxChains ? nch - c0 : kMaxChains;
     memcpy(ct.c, p.chains.data() + c0, sizeof(Chain) * ct.count);
+    ScopedTiming tm(0, st);
     CBF_CUDA(p.ops->bm_forward(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, ws,
                                ws.fpart_bm + (size_t)c0 * p.ptiles, st));
   }
-  CBF_CUDA(p.ops->fw_forward(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, ws, ws.fpart_fw, st));
+  {
+    ScopedTiming tm(1, st);
+    CBF_CUDA(p.ops->fw_forward(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, ws, ws.fpart_fw, st));
+  }
   finalize_terms_kernel<<<1, 256, 0, st>>>(ws.fpart_bm, nch * p.ptiles, ws.fpart_fw, p.ptiles, p.dy, var_y,
                                            (double)p.D.n_local * p.D.T, ws.stats, terms);
   CBF_CUDA(cudaGetLastError());
@@ -472,7 +504,10 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
 
   // reverse of the forward rollout (writes the y2 adjoints), then of the message chains
   const int grid_f = rev_grid(p, 2, p.ptiles);
-  CBF_CUDA(p.ops->fw_reverse(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, ws.gpart_f, grid_f, st));
+  {
+    ScopedTiming tm(2, st);
+    CBF_CUDA(p.ops->fw_reverse(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, ws.gpart_f, grid_f, st));
+  }
   reduce_slots_kernel<<<ceil_div(p.Lf.slot(), 256), 256, 0, st>>>(ws.gpart_f, grid_f, p.Lf.slot(), ws.acc_f);
   CBF_CUDA(cudaGetLastError());
 
@@ -485,8 +520,11 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
     int grid_b = rev_grid(p, 3, p.ptiles * ct.count);
     if (nslots_b + grid_b > kMaxGridRev) grid_b = kMaxGridRev - nslots_b;
     if (grid_b < 1) { set_error("too many chain batches"); return CBF_ERR_INVALID_SHAPE; }
-    CBF_CUDA(p.ops->bm_reverse(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, w_en, ws,
-                               ws.gpart_b + (size_t)nslots_b * p.Lb.slot(), grid_b, st));
+    {
+      ScopedTiming tm(3, st);
+      CBF_CUDA(p.ops->bm_reverse(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, w_en, ws,
+                                 ws.gpart_b + (size_t)nslots_b * p.Lb.slot(), grid_b, st));
+    }
     nslots_b += grid_b;
   }
   reduce_slots_kernel<<<ceil_div(p.Lb.slot(), 256), 256, 0, st>>>(ws.gpart_b, nslots_b, p.Lb.slot(), ws.acc_b);
@@ -546,6 +584,27 @@ CBF_API int cbf_adam_step(int64_t n, double *theta, const double *grad, double *
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, theta, grad, m, v, lr_t,
                                                                                          beta1, beta2, eps);
   CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+CBF_API int cbf_timing_enable(int enable) {
+  g_timing.enabled = enable != 0;
+  g_timing.used = 0;
+  return 0;
+}
+
+CBF_API int cbf_timing_read(double *ms_sum_host, int64_t *count_host) {
+  if (!ms_sum_host || !count_host) { set_error("cbf_timing_read: NULL argument"); return CBF_ERR_NULL; }
+  for (int k = 0; k < 4; ++k) { ms_sum_host[k] = 0.0; count_host[k] = 0; }
+  TimingPool &t = g_timing;
+  for (size_t i = 0; i < t.used; ++i) {
+    CBF_CUDA(cudaEventSynchronize(t.ev[2 * i + 1]));
+    float ms = 0.f;
+    CBF_CUDA(cudaEventElapsedTime(&ms, t.ev[2 * i], t.ev[2 * i + 1]));
+    ms_sum_host[t.kind[i]] += ms;
+    count_host[t.kind[i]] += 1;
+  }
+  t.used = 0;
   return 0;
 }
 

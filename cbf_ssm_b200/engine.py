@@ -91,6 +91,20 @@ def init_param_arrays(d: ModelDims, config: dict, seed: Optional[int] = None) ->
     return out
 
 
+def count_chain_batches(T, R, per_launch=120):
+    """Launches the backward-message kernels need: live chain segments of both runs
+    (cbfssm.py:123-136), at most ``per_launch`` per launch (csrc/common.cuh kMaxChains)."""
+    n = 0
+    for run in (0, 1):
+        off = 1 if run == 0 else R + 1
+        starts = [T - 1] + [t for t in range(T - 2, -1, -1) if (t + off) % (2 * R) == 0]
+        for i, t_hi in enumerate(starts):
+            t_next = starts[i + 1] if i + 1 < len(starts) else -1
+            if any(((t % (2 * R)) < R) == (run == 0) for t in range(t_hi, t_next, -1)):
+                n += 1
+    return max(1, -(-n // per_launch)) if n else 0
+
+
 class _GpBuffers:
     """float32 operands + float64 prologue state of one GP."""
 
@@ -140,6 +154,7 @@ class ElboEngine:
         self._gflat = None
         self._shape = None
         self._saved = None
+        self.launches = 0          # kernels of this library launched so far (bench.py gpu_launches)
 
     # ---------------- parameters ----------------
     def view(self, name, of=None):
@@ -190,6 +205,7 @@ class ElboEngine:
             check(lib.cbf_gp_prologue(g.M, g.din, g.dout, *(ptr(self.view(f"{tag}.{f}")) for f in GP_FIELDS),
                                       ptr(g.Z), ptr(g.ell), ptr(g.sig2), ptr(g.P), ptr(g.alpha), ptr(g.S),
                                       ptr(g.kl), ptr(g.state), st))
+        self.launches += 3
 
     def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True):
         """u [B,T,du], y [B,T,dy] float32 device tensors; draws float32 device tensors
@@ -206,6 +222,8 @@ class ElboEngine:
                                         ptr(eps_f), ptr(self.terms), ptr(self._ws), self._stream()))
         self._shape = shape
         self._saved = (u, y, eps_b, z_b, eps_f)
+        self._nb = count_chain_batches(T, self.dims.recog_len)
+        self.launches += self._nb + 2
         return self.loss_terms(self.terms)
 
     def loss_terms(self, terms):
@@ -241,6 +259,7 @@ class ElboEngine:
                                                *(gat(f"{tag}.{f}") for f in GP_FIELDS), st))
         check(lib.cbf_noise_backward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
                                      at(gl.var_x), at(gl.var_y), gat("var_x_unc"), gat("var_y_unc"), st))
+        self.launches += 6 + self._nb + 3
         return self.grad
 
     def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -248,6 +267,7 @@ class ElboEngine:
         self.adam_t += 1
         check(self.lib.cbf_adam_step(self.theta.numel(), ptr(self.theta), ptr(self.grad), ptr(self.adam_m),
                                      ptr(self.adam_v), self.adam_t, float(lr), beta1, beta2, eps, self._stream()))
+        self.launches += 1
 
     def export_states(self, y):
         """x_final, y_tilde as [nb, T, S, dx] float32 (cbfssm.py:97,181) of the last forward."""
@@ -268,6 +288,7 @@ class ElboEngine:
 
     def fill_normal(self, out, seed, stream_id):
         check(self.lib.cbf_fill_normal(ptr(out), out.numel(), int(seed), int(stream_id), self._stream()))
+        self.launches += 1
         return out
 
     def kernel_level_grads(self):

@@ -161,6 +161,15 @@ CBF_API int cbf_adam_step(int64_t n, double *theta, const double *grad, double *
  * cbfssm.py:134,149,209): Philox4x32-10 + Box-Muller, counter = element index. */
 CBF_API int cbf_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t stream_id, void *stream);
 
+/* Measurement aid for bench.py (the only thread-local state the library keeps, off by
+ * default): when enabled, the four rollout kernels (0 backward-message forward,
+ * 1 forward rollout, 2 forward-rollout reverse, 3 backward-message reverse) are
+ * bracketed by CUDA events on the caller's stream.  cbf_timing_read synchronises on
+ * those events and returns the summed milliseconds and launch counts per kernel since
+ * the last read. */
+CBF_API int cbf_timing_enable(int enable);
+CBF_API int cbf_timing_read(double *ms_sum_host /*[4]*/, int64_t *count_host /*[4]*/);
+
 #ifdef __cplusplus
 }
 #endif
