@@ -27,7 +27,7 @@ class cbf_shape(C.Structure):
     _fields_ = [("B", C.c_int32), ("S", C.c_int32), ("T", C.c_int32), ("M", C.c_int32),
                 ("dx", C.c_int32), ("du", C.c_int32), ("dy", C.c_int32), ("R", C.c_int32),
                 ("condition", C.c_int32), ("n_offset", C.c_int32), ("n_local", C.c_int32),
-                ("k_factor", C.c_float)]
+                ("k_factor", C.c_float), ("flags", C.c_int32)]
 
 
 class cbf_gp(C.Structure):

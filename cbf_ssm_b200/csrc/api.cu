@@ -22,7 +22,17 @@ void set_error(const char *fmt, ...) {
 CBF_DIMS_LIST(CBF_DECLARE_OPS)
 #undef CBF_DECLARE_OPS
 
-const DimOps *find_ops(int dx, int du, int dy) {
+#define CBF_DECLARE_FAST(DX, DU, DY, M) const DimOps *fast_ops_##DX##_##DU##_##DY##_##M();
+CBF_FAST_LIST(CBF_DECLARE_FAST)
+#undef CBF_DECLARE_FAST
+
+const DimOps *find_ops(int dx, int du, int dy, int M, bool allow_fast) {
+  if (allow_fast) {
+#define CBF_MATCH_FAST(DX, DU, DY, MM) \
+  if (dx == DX && du == DU && dy == DY && M == MM) return fast_ops_##DX##_##DU##_##DY##_##MM();
+    CBF_FAST_LIST(CBF_MATCH_FAST)
+#undef CBF_MATCH_FAST
+  }
 #define CBF_MATCH_OPS(DX, DU, DY) \
   if (dx == DX && du == DU && dy == DY) return ops_##DX##_##DU##_##DY();
   CBF_DIMS_LIST(CBF_MATCH_OPS)
@@ -87,7 +97,7 @@ static std::vector<Chain> build_chains(int T, int R) {
 struct Plan {
   Dims D;
   int dx, du, dy, dh, din;
-  int ptiles;
+  int ptiles, slots_per_cta;
   std::vector<Chain> chains;
   AccLayout Lf, Lb;
   size_t off_X, off_H, off_Yb, off_fbm, off_ffw, off_gf, off_gb, off_accf, off_accb, off_stats, total;
@@ -105,7 +115,7 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
     return CBF_ERR_INVALID_SHAPE;
   }
   p.dx = s->dx; p.du = s->du; p.dy = s->dy; p.dh = s->dx - s->dy; p.din = s->dx + s->du;
-  p.ops = find_ops(s->dx, s->du, s->dy);
+  p.ops = find_ops(s->dx, s->du, s->dy, s->M, !(s->flags & CBF_FLAG_FORCE_COOPERATIVE));
   if (need_ops && !p.ops) {
     set_error("dims (dx=%d,du=%d,dy=%d) are not compiled in (see csrc/dims_list.h)", s->dx, s->du, s->dy);
     return CBF_ERR_UNSUPPORTED_DIMS;
@@ -122,10 +132,17 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   D.B = s->B; D.S = s->S; D.T = s->T; D.M = s->M; D.R = s->R; D.condition = s->condition ? 1 : 0;
   D.n_offset = s->n_offset; D.n_local = s->n_local; D.kap = s->k_factor;
   D.npad = round_up(s->n_local, 32);
-  p.ptiles = ceil_div(s->n_local, kNP);
+  p.ptiles = ceil_div(s->n_local, kNP);            // upper bound for every path (smallest CTA tile)
   p.chains = build_chains(s->T, s->R);
-  p.Lf = AccLayout(s->M, p.din, p.dx, p.dx);
-  p.Lb = AccLayout(s->M, p.din, p.dh, p.dx);
+  p.slots_per_cta = 1;
+  if (p.ops) {
+    p.ops->layouts(s->M, &p.Lf, &p.Lb);
+    p.slots_per_cta = p.ops->slots_per_cta;
+    p.ptiles = ceil_div(s->n_local, p.ops->particles_per_cta);
+  } else {
+    p.Lf = AccLayout(s->M, p.din, p.dx, p.dx);
+    p.Lb = AccLayout(s->M, p.din, p.dh, p.dx);
+  }
   size_t o = 0;
   const size_t np = D.npad;
   p.off_X = o; o = align_up(o + sizeof(float) * s->T * p.dx * np, 256);
@@ -133,8 +150,8 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   p.off_Yb = o; o = align_up(o + sizeof(float) * s->T * p.dh * np, 256);
   p.off_fbm = o; o = align_up(o + sizeof(float) * p.chains.size() * p.ptiles, 256);
   p.off_ffw = o; o = align_up(o + sizeof(float) * p.ptiles * (p.dy + 1), 256);
-  p.off_gf = o; o = align_up(o + sizeof(float) * (size_t)kMaxGridRev * p.Lf.slot(), 256);
-  p.off_gb = o; o = align_up(o + sizeof(float) * (size_t)kMaxGridRev * p.Lb.slot(), 256);
+  p.off_gf = o; o = align_up(o + sizeof(float) * (size_t)kMaxGridRev * p.slots_per_cta * p.Lf.slot(), 256);
+  p.off_gb = o; o = align_up(o + sizeof(float) * (size_t)kMaxGridRev * p.slots_per_cta * p.Lb.slot(), 256);
   p.off_accf = o; o = align_up(o + sizeof(double) * p.Lf.slot(), 256);
   p.off_accb = o; o = align_up(o + sizeof(double) * p.Lb.slot(), 256);
   p.off_stats = o; o = align_up(o + sizeof(double) * (p.dy + 2), 256);
@@ -233,26 +250,23 @@ __global__ void finalize_gp_grad_kernel(AccLayout L, const double *__restrict__ 
                                         double *__restrict__ gP, double *__restrict__ galpha,
                                         double *__restrict__ gS, double *__restrict__ gZ,
                                         double *__restrict__ gell, double *__restrict__ gsig2) {
-  const int M = L.M, MG = L.MG, DG = L.DG, CG = L.CG, Din = L.Din, Dout = L.Dout;
-  auto at = [&](int m, int col) -> double {
-    const int rg = m >> 2, r = m & 3, cg = col >> 2, c = col & 3;
-    return acc[((size_t)r * L.ntiles + (rg * CG + cg)) * 4 + c];
-  };
+  const int M = L.M, Din = L.Din, Dout = L.Dout;
+  auto at = [&](int m, int col) -> double { return acc[L.index(m, col)]; };
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int i = tid; i < M * M; i += nt) gP[i] = at(i / M, i % M);
   for (int i = tid; i < M * Dout; i += nt) {
     const int m = i / Dout, d = i % Dout;
-    galpha[i] = at(m, 4 * MG + d);
-    gS[i] = at(m, 4 * (MG + DG) + d);
+    galpha[i] = at(m, L.colGm + d);
+    gS[i] = at(m, L.colGv + d);
   }
-  const int xc = 4 * (MG + 2 * DG);
+  const int xc = L.colX;
   for (int i = tid; i < M * Din; i += nt) {
     const int m = i / Din, j = i % Din;
     const double ell = (double)gp.ell[j];
     const double zt = (double)gp.Z[i] / ell;
     gZ[i] = (at(m, xc + j) - zt * at(m, xc + Din)) / ell;
   }
-  const double *sc = acc + L.nacc;
+  const double *sc = acc + L.scal_off();
   for (int j = tid; j < Din; j += nt) gell[j] = sc[j] / (double)gp.ell[j];
   if (tid == 0) gsig2[0] = sc[Din] / (double)gp.sig2[0] + sc[Din + 1];
 }
@@ -425,7 +439,7 @@ CBF_API int cbf_abi_version(void) { return CBF_ABI_VERSION; }
 CBF_API const char *cbf_last_error_string(void) { return g_err; }
 
 CBF_API int cbf_supported(int32_t M, int32_t dx, int32_t du, int32_t dy) {
-  const DimOps *ops = find_ops(dx, du, dy);
+  const DimOps *ops = find_ops(dx, du, dy, M, true);
   if (!ops || M < 1) return 0;
   for (int w = 0; w < 4; ++w)
     if (ops->smem_bytes(M, w) > kMaxSmem) return 0;
@@ -508,7 +522,8 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
     ScopedTiming tm(2, st);
     CBF_CUDA(p.ops->fw_reverse(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, ws.gpart_f, grid_f, st));
   }
-  reduce_slots_kernel<<<ceil_div(p.Lf.slot(), 256), 256, 0, st>>>(ws.gpart_f, grid_f, p.Lf.slot(), ws.acc_f);
+  reduce_slots_kernel<<<ceil_div(p.Lf.slot(), 256), 256, 0, st>>>(ws.gpart_f, grid_f * p.slots_per_cta, p.Lf.slot(),
+                                                                  ws.acc_f);
   CBF_CUDA(cudaGetLastError());
 
   const int nch = (int)p.chains.size();
@@ -523,11 +538,12 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
     {
       ScopedTiming tm(3, st);
       CBF_CUDA(p.ops->bm_reverse(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, w_en, ws,
-                                 ws.gpart_b + (size_t)nslots_b * p.Lb.slot(), grid_b, st));
+                                 ws.gpart_b + (size_t)nslots_b * p.slots_per_cta * p.Lb.slot(), grid_b, st));
     }
     nslots_b += grid_b;
   }
-  reduce_slots_kernel<<<ceil_div(p.Lb.slot(), 256), 256, 0, st>>>(ws.gpart_b, nslots_b, p.Lb.slot(), ws.acc_b);
+  reduce_slots_kernel<<<ceil_div(p.Lb.slot(), 256), 256, 0, st>>>(ws.gpart_b, nslots_b * p.slots_per_cta, p.Lb.slot(),
+                                                                  ws.acc_b);
   CBF_CUDA(cudaGetLastError());
 
   finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lf, ws.acc_f, to_dev(gp_f), grad_flat + gl.f_P, grad_flat + gl.f_alpha,
@@ -537,7 +553,7 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
                                              grad_flat + gl.b_S, grad_flat + gl.b_Z, grad_flat + gl.b_ell,
                                              grad_flat + gl.b_sig2);
   finalize_noise_grad_kernel<<<1, 32 * ceil_div(p.dx, 32), 0, st>>>(
-      p.dx, p.dy, p.din, ws.acc_f + p.Lf.nacc, ws.acc_b + p.Lb.nacc, ws.stats, var_y, (double)term_weights_host[0],
+      p.dx, p.dy, p.din, ws.acc_f + p.Lf.scal_off(), ws.acc_b + p.Lb.scal_off(), ws.stats, var_y, (double)term_weights_host[0],
       (double)p.D.n_local * p.D.T, grad_flat + gl.var_x, grad_flat + gl.var_y);
   CBF_CUDA(cudaGetLastError());
   return 0;

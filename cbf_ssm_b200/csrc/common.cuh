@@ -55,21 +55,38 @@ struct Dims {
 
 inline __host__ __device__ int writer_run(int t, int R) { return (t % (2 * R)) < R ? 0 : 1; }
 
-// Layout of one reverse-pass accumulator block for a GP with (M, Din, Dout):
-// tiles of 4x4 outputs, index = (r * ntiles + tile) * 4 + c, tile = rg * CG + cg.
+// Layout of one reverse-pass accumulator block for a GP with (M, Din, Dout).
+// The parameter adjoints are one outer-product accumulation  ACC[m][col] += left[m] * right[col]
+// over (particle, step), with the "right" vector [k (M) | g_mean (Dout) | g_var (Dout) | x~ (Din), 1]
+// and the left vector chosen per column block (a_bar | k | a^2 | w | w).  It is tiled TR x TC;
+// each column block is padded to a multiple of TC.
+//   interleaved = 0 (cooperative path): index = (i * ntiles + tile) * TC + j      (TR = TC = 4)
+//   interleaved = 1 (register path)   : index = (tile * TR + i) * TC + j
 struct AccLayout {
-  int M, MP, MG, Din, Dout, DG, XG, CG, ntiles, nacc;  // nacc = ntiles*16
-  int nscal;                                           // per-CTA scalar sums appended after the tiles
+  int M, Din, Dout, TR, TC, interleaved;
+  int RG, CGk, CGd, CGx, CG, ntiles, nacc;
+  int colK, colGm, colGv, colX, ncols;   // first padded column of each block
+  int nscal;                             // per-CTA scalar sums appended after the tiles
+  // legacy names used by the cooperative kernels
+  int MP, MG, DG, XG;
   __host__ __device__ AccLayout() {}
-  __host__ __device__ AccLayout(int M_, int Din_, int Dout_, int dx) {
-    M = M_; Din = Din_; Dout = Dout_;
-    MP = round_up(M, 4); MG = MP / 4;
-    DG = ceil_div(Dout, 4); XG = ceil_div(Din + 1, 4);
-    CG = MG + 2 * DG + XG;
-    ntiles = MG * CG; nacc = ntiles * 16;
+  __host__ __device__ AccLayout(int M_, int Din_, int Dout_, int dx, int TR_ = 4, int TC_ = 4, int inter = 0) {
+    M = M_; Din = Din_; Dout = Dout_; TR = TR_; TC = TC_; interleaved = inter;
+    RG = ceil_div(M, TR);
+    CGk = ceil_div(M, TC); CGd = ceil_div(Dout, TC); CGx = ceil_div(Din + 1, TC);
+    CG = CGk + 2 * CGd + CGx;
+    ntiles = RG * CG; nacc = ntiles * TR * TC;
+    colK = 0; colGm = CGk * TC; colGv = colGm + CGd * TC; colX = colGv + CGd * TC; ncols = CG * TC;
     nscal = Din + 2 + 2 * dx;   // L_j[Din], sum w, sum G, var_x_bar[dx], var_y_bar[dx]
+    MP = round_up(M, 4); MG = MP / 4; DG = CGd; XG = CGx;
   }
-  __host__ __device__ int slot() const { return nacc + round_up(nscal, 4); }
+  __host__ __device__ int slot() const { return round_up(nacc, 4) + round_up(nscal, 4); }
+  __host__ __device__ int scal_off() const { return round_up(nacc, 4); }
+  __host__ __device__ size_t index(int m, int col) const {
+    const int rg = m / TR, i = m - rg * TR, cg = col / TC, j = col - cg * TC;
+    const int tile = rg * CG + cg;
+    return interleaved ? ((size_t)tile * TR + i) * TC + j : ((size_t)i * ntiles + tile) * TC + j;
+  }
 };
 
 // Kernel entry points of one (dx,du,dy) instantiation, filled by CBF_INSTANTIATE.
@@ -88,9 +105,14 @@ struct DimOps {
                             float *part_out, int grid, cudaStream_t);
   size_t (*smem_bytes)(int M, int which);  // which: 0 bm_fwd 1 fw_fwd 2 fw_rev 3 bm_rev
   int (*occupancy)(int M, int which);      // resident CTAs/SM of the persistent reverse kernels
+  void (*layouts)(int M, AccLayout *Lf, AccLayout *Lb);   // accumulator layouts of the two reverse kernels
+  int slots_per_cta;                       // partial-sum slots each reverse CTA writes
+  int particles_per_cta;                   // particle tile of one CTA
+  int fixed_M;                             // 0: any M (cooperative path); else the compiled-in M
 };
 
-const DimOps *find_ops(int dx, int du, int dy);
+// Register-resident ops for (dx,du,dy,M) if compiled in and allowed, else the cooperative ops.
+const DimOps *find_ops(int dx, int du, int dy, int M, bool allow_fast);
 
 void set_error(const char *fmt, ...);
 

@@ -1,0 +1,697 @@
+// Register-resident kernel path for small M (compile-time M <= 32): one thread = one particle.
+//
+// The resident GP operands (P = K_zz^-1, Z/ell, alpha, S) sit in shared memory and are read
+// with warp-uniform (broadcast) vector loads; the particle's M-vectors k, a = P k, b live in
+// registers with fully unrolled, statically indexed loops; particle state streams through
+// registers with coalesced [t][dim][n] global accesses.  No block-level synchronisation on
+// the rollout itself.  The parameter adjoints (P_bar += a_bar k^T, ...) are accumulated per
+// WARP: each lane stages its particle's vectors into a warp-private K-major shared tile, then
+// the 32 lanes own TR x TC register tiles of the outer-product accumulation over the warp's
+// 32 particles -- only __syncwarp() is needed and the accumulators stay in registers for the
+// whole launch.  (TR, TC) is chosen at compile time per (M, Din, Dout).
+//
+// Mathematics: SURVEY.md 8a notes 1-5; verified in float64 by oracle/kernel_math.py.
+#pragma once
+#include "common.cuh"
+#include "step_math.cuh"
+
+namespace cbf {
+
+constexpr int kFastThreads = 128;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kSLD = 36;   // staging row stride (floats): 32 lanes + 4, == 4 mod 32
+
+struct TileCfg {
+  int TR, TC, rounds;
+};
+
+constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Compiler-only memory barrier.  The resident operands in shared memory are loop-invariant,
+// so without it the compiler hoists / CSEs hundreds of shared loads out of the time loop
+// (and from the first contraction into the second) and then spills them.
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+
+// Minimise issue slots per particle-step of the per-warp accumulation: rounds * (TR*TC FMAs + loads).
+constexpr TileCfg pick_tiles(int M, int Din, int Dout) {
+  TileCfg best{4, 4, 1000};
+  double best_cost = 1e30;
+  for (int tr = 2; tr <= 8; ++tr)
+    for (int tc = 2; tc <= 8; ++tc) {
+      const int rg = cdiv(M, tr), cg = cdiv(M, tc) + 2 * cdiv(Dout, tc) + cdiv(Din + 1, tc);
+      const int rounds = cdiv(rg * cg, 32);
+      if (rounds * tr * tc > 50) continue;   // accumulator registers per lane
+      const double cost = rounds * (tr * tc + 0.5 * (tr + tc));
+      if (cost < best_cost) { best_cost = cost; best = TileCfg{tr, tc, rounds}; }
+    }
+  return best;
+}
+
+// Shared-memory image of one GP's operands, compile-time sizes.
+template <int M, int DIN, int DOUT>
+struct GpF {
+  static constexpr int MP = (M + 3) / 4 * 4;
+  static constexpr int DINP = (DIN + 3) / 4 * 4;
+  static constexpr int DOUTP = (DOUT + 3) / 4 * 4;
+  static constexpr int FLOATS = MP * MP + MP * (DINP + 2 * DOUTP) + DINP + 4;
+  const float *P, *Zt, *al, *Sm, *il;
+  float sig2, lsig;
+
+  __device__ float *init(float *base, const GpDev &g) {
+    float *Pw = base; base += MP * MP;
+    float *Zw = base; base += MP * DINP;
+    float *aw = base; base += MP * DOUTP;
+    float *Sw = base; base += MP * DOUTP;
+    float *iw = base; base += DINP + 4;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < MP * MP; i += nt) {
+      const int r = i / MP, c = i % MP;
+      Pw[i] = (r < M && c < M) ? g.P[r * M + c] : 0.f;
+    }
+    for (int i = tid; i < MP * DINP; i += nt) {
+      const int r = i / DINP, c = i % DINP;
+      Zw[i] = (r < M && c < DIN) ? g.Z[r * DIN + c] / g.ell[c] : 0.f;
+    }
+    for (int i = tid; i < MP * DOUTP; i += nt) {
+      const int r = i / DOUTP, c = i % DOUTP;
+      const bool ok = (r < M && c < DOUT);
+      aw[i] = ok ? g.alpha[r * DOUT + c] : 0.f;
+      Sw[i] = ok ? g.S[r * DOUT + c] : 0.f;
+    }
+    for (int i = tid; i < DINP; i += nt) iw[i] = (i < DIN) ? 1.f / g.ell[i] : 0.f;
+    P = Pw; Zt = Zw; al = aw; Sm = Sw; il = iw;
+    sig2 = g.sig2[0];
+    lsig = log2f(sig2);
+    return base;
+  }
+};
+
+template <int N>
+__device__ __forceinline__ void ld_row(const float *__restrict__ p, float (&v)[N]) {
+  static_assert(N % 4 == 0, "rows are padded to float4");
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 t = *reinterpret_cast<const float4 *>(p + i);
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  }
+}
+
+// a = P k for the thread's particle, 4 rows at a time (independent FMA chains).
+template <int MP>
+__device__ __forceinline__ void matvec_fast(const float *__restrict__ P, const float (&k)[MP], float (&a)[MP]) {
+#pragma unroll
+  for (int m0 = 0; m0 < MP; m0 += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int mp = 0; mp < MP; mp += 4) {
+      const float4 p0 = *reinterpret_cast<const float4 *>(P + (m0 + 0) * MP + mp);
+      const float4 p1 = *reinterpret_cast<const float4 *>(P + (m0 + 1) * MP + mp);
+      const float4 p2 = *reinterpret_cast<const float4 *>(P + (m0 + 2) * MP + mp);
+      const float4 p3 = *reinterpret_cast<const float4 *>(P + (m0 + 3) * MP + mp);
+      a0 = fmaf(p0.x, k[mp], a0); a0 = fmaf(p0.y, k[mp + 1], a0); a0 = fmaf(p0.z, k[mp + 2], a0); a0 = fmaf(p0.w, k[mp + 3], a0);
+      a1 = fmaf(p1.x, k[mp], a1); a1 = fmaf(p1.y, k[mp + 1], a1); a1 = fmaf(p1.z, k[mp + 2], a1); a1 = fmaf(p1.w, k[mp + 3], a1);
+      a2 = fmaf(p2.x, k[mp], a2); a2 = fmaf(p2.y, k[mp + 1], a2); a2 = fmaf(p2.z, k[mp + 2], a2); a2 = fmaf(p2.w, k[mp + 3], a2);
+      a3 = fmaf(p3.x, k[mp], a3); a3 = fmaf(p3.y, k[mp + 1], a3); a3 = fmaf(p3.z, k[mp + 2], a3); a3 = fmaf(p3.w, k[mp + 3], a3);
+    }
+    a[m0] = a0; a[m0 + 1] = a1; a[m0 + 2] = a2; a[m0 + 3] = a3;
+  }
+}
+
+// One sparse-GP evaluation (gp_tf.py:132-161) for the thread's particle.
+template <int M, int DIN, int DOUT>
+__device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT> &g, const float (&xin)[DIN],
+                                                float (&xt)[GpF<M, DIN, DOUT>::DINP],
+                                                float (&k)[GpF<M, DIN, DOUT>::MP], float (&a)[GpF<M, DIN, DOUT>::MP],
+                                                float (&fm)[DOUT], float (&fv)[DOUT]) {
+  using G = GpF<M, DIN, DOUT>;
+  constexpr int MP = G::MP, DINP = G::DINP, DOUTP = G::DOUTP;
+  {
+    float il[DINP];
+    ld_row<DINP>(g.il, il);
+#pragma unroll
+    for (int j = 0; j < DINP; ++j) xt[j] = (j < DIN) ? xin[j < DIN ? j : 0] * il[j] : 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) fm[d] = 0.f;
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    if (m < M) {
+      float z[DINP];
+      ld_row<DINP>(g.Zt + m * DINP, z);
+      float d2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < DIN; ++j) { const float e = xt[j] - z[j]; d2 = fmaf(e, e, d2); }
+      k[m] = exp2f(fmaf(kNegHalfLog2e, d2, g.lsig));
+      float al[DOUTP];
+      ld_row<DOUTP>(g.al + m * DOUTP, al);
+#pragma unroll
+      for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(k[m], al[d], fm[d]);
+    } else {
+      k[m] = 0.f;
+    }
+  }
+  matvec_fast<MP>(g.P, k, a);
+  float q = 0.f;
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    q = fmaf(k[m], a[m], q);
+    const float a2 = a[m] * a[m];
+    float S[DOUTP];
+    ld_row<DOUTP>(g.Sm + m * DOUTP, S);
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, S[d], fv[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) fv[d] = g.sig2 - q + fv[d];
+}
+
+// ---- per-warp staging tile + accumulation of the parameter adjoints ----
+// Row map of the warp-private staging tile (each row = 32 lanes, stride kSLD):
+//   right matrix: [k : colGm rows (zero padded)] [g_mean : CGd*TC] [g_var : CGd*TC] [x~,1 : CGx*TC]
+//   left-only   : [a_bar : RG*TR] [a^2 : RG*TR] [w : RG*TR]     (k doubles as a left operand)
+template <int M, int DIN, int DOUT>
+struct WarpAcc {
+  static constexpr TileCfg TCFG = pick_tiles(M, DIN, DOUT);
+  static constexpr int TR = TCFG.TR, TC = TCFG.TC, ROUNDS = TCFG.rounds;
+  static constexpr int RG = cdiv(M, TR), CGk = cdiv(M, TC), CGd = cdiv(DOUT, TC), CGx = cdiv(DIN + 1, TC);
+  static constexpr int CG = CGk + 2 * CGd + CGx, NTILES = RG * CG;
+  static constexpr int KROWS = (CGk * TC > RG * TR) ? CGk * TC : RG * TR;
+  static constexpr int rowK = 0, rowGm = KROWS, rowGv = rowGm + CGd * TC, rowX = rowGv + CGd * TC;
+  static constexpr int rowAb = rowX + CGx * TC, rowAsq = rowAb + RG * TR, rowW = rowAsq + RG * TR;
+  static constexpr int ROWS = rowW + RG * TR;
+  static constexpr int FLOATS = ROWS * kSLD;
+  static constexpr int NACC = NTILES * TR * TC;
+
+  float acc[ROUNDS][TR][TC];
+  int loff[ROUNDS], roff[ROUNDS];   // staging row offsets (floats) of this lane's tiles
+
+  __device__ __forceinline__ void init(int lane) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int j = 0; j < TC; ++j) acc[r][i][j] = 0.f;
+      int tile = lane + 32 * r;
+      if (tile >= NTILES) tile = 0;   // idle slot: recompute tile 0, never written out
+      const int rg = tile / CG, cg = tile - rg * CG;
+      int lrow, rrow;
+      if (cg < CGk) { lrow = rowAb; rrow = rowK + cg * TC; }
+      else if (cg < CGk + CGd) { lrow = rowK; rrow = rowGm + (cg - CGk) * TC; }
+      else if (cg < CGk + 2 * CGd) { lrow = rowAsq; rrow = rowGv + (cg - CGk - CGd) * TC; }
+      else { lrow = rowW; rrow = rowX + (cg - CGk - 2 * CGd) * TC; }
+      loff[r] = (lrow + rg * TR) * kSLD;
+      roff[r] = rrow * kSLD;
+    }
+  }
+
+  // stg holds this step's vectors of the warp's 32 particles (all lanes have written + __syncwarp).
+  __device__ __forceinline__ void accumulate(const float *__restrict__ stg) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const float *lp = stg + loff[r], *rp = stg + roff[r];
+#pragma unroll 2
+      for (int n4 = 0; n4 < 32; n4 += 4) {
+        float4 l[TR], rr[TC];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) l[i] = *reinterpret_cast<const float4 *>(lp + i * kSLD + n4);
+#pragma unroll
+        for (int j = 0; j < TC; ++j) rr[j] = *reinterpret_cast<const float4 *>(rp + j * kSLD + n4);
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+          for (int j = 0; j < TC; ++j) {
+            float c = acc[r][i][j];
+            c = fmaf(l[i].x, rr[j].x, c);
+            c = fmaf(l[i].y, rr[j].y, c);
+            c = fmaf(l[i].z, rr[j].z, c);
+            c = fmaf(l[i].w, rr[j].w, c);
+            acc[r][i][j] = c;
+          }
+      }
+    }
+  }
+
+  __device__ __forceinline__ void store(float *__restrict__ out, int lane) const {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int tile = lane + 32 * r;
+      if (tile < NTILES) {
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+          for (int j = 0; j < TC; ++j) out[((size_t)tile * TR + i) * TC + j] = acc[r][i][j];
+      }
+    }
+  }
+};
+
+// Reverse of one GP evaluation (SURVEY 8a note 4) for the thread's particle; stages the
+// outer-product operands into the warp tile.  k, a from gp_forward_fast.
+template <int M, int DIN, int DOUT, int NEED>
+__device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT> &g, float *__restrict__ stg, int lane,
+                                                const float (&xt)[GpF<M, DIN, DOUT>::DINP],
+                                                const float (&k)[GpF<M, DIN, DOUT>::MP],
+                                                const float (&a)[GpF<M, DIN, DOUT>::MP], const float (&gm)[DOUT],
+                                                const float (&gv)[DOUT], bool live, float (&xinb)[NEED],
+                                                float (&Lacc)[DIN], float &sw, float &sG) {
+  using G = GpF<M, DIN, DOUT>;
+  using W = WarpAcc<M, DIN, DOUT>;
+  constexpr int MP = G::MP, DINP = G::DINP, DOUTP = G::DOUTP;
+  float Gs = 0.f;
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) Gs += gv[d];
+  sG += Gs;
+  float b[MP];
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    if (m < M) {
+      float S[DOUTP];
+      ld_row<DOUTP>(g.Sm + m * DOUTP, S);
+      float c = 0.f;
+#pragma unroll
+      for (int d = 0; d < DOUT; ++d) c = fmaf(S[d], gv[d], c);
+      b[m] = a[m] * c;
+    } else {
+      b[m] = 0.f;
+    }
+  }
+  float pb[MP];
+  compiler_fence();
+  matvec_fast<MP>(g.P, b, pb);
+  compiler_fence();
+#pragma unroll
+  for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
+  float *sp = stg + lane;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    float al[DOUTP];
+    ld_row<DOUTP>(g.al + m * DOUTP, al);
+    float kb = 2.f * pb[m] - 2.f * Gs * a[m];
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gm[d], kb);
+    const float w = kb * k[m];
+    sw += w;
+    float z[DINP];
+    ld_row<DINP>(g.Zt + m * DINP, z);
+#pragma unroll
+    for (int j = 0; j < DIN; ++j) {
+      const float dl = xt[j] - z[j];
+      const float wd = w * dl;
+      if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
+      Lacc[j] = fmaf(wd, dl, Lacc[j]);
+    }
+    sp[(W::rowK + m) * kSLD] = k[m];
+    sp[(W::rowAb + m) * kSLD] = 2.f * b[m] - Gs * k[m];
+    sp[(W::rowAsq + m) * kSLD] = a[m] * a[m];
+    sp[(W::rowW + m) * kSLD] = w;
+  }
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) {
+    sp[(W::rowGm + d) * kSLD] = gm[d];
+    sp[(W::rowGv + d) * kSLD] = gv[d];
+  }
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) sp[(W::rowX + j) * kSLD] = live ? xt[j] : 0.f;
+  sp[(W::rowX + DIN) * kSLD] = live ? 1.f : 0.f;
+  {
+    float il[DINP];
+    ld_row<DINP>(g.il, il);
+#pragma unroll
+    for (int j = 0; j < NEED; ++j) xinb[j] *= il[j];
+  }
+}
+
+// Sum `count` per-thread floats over the CTA; thread 0 writes out[0..count).
+template <int COUNT>
+__device__ __forceinline__ void cta_sum_store(const float (&vals)[COUNT], float *scratch, float *out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < COUNT; ++i) {
+    float v = vals[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) scratch[i * kFastWarps + warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < COUNT; ++i) {
+      float s = 0.f;
+      for (int w = 0; w < kFastWarps; ++w) s += scratch[i * kFastWarps + w];
+      out[i] = s;
+    }
+  }
+}
+
+// =====================================================================================
+template <int DX, int DU, int DY, int M>
+__global__ void __launch_bounds__(kFastThreads) bm_forward_fast_kernel(
+    Dims D, ChainTable chains, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ u,
+    const float *__restrict__ y, const float *__restrict__ eps_b, const float *__restrict__ z_b, Workspace ws,
+    float *__restrict__ part_out) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  using G = GpF<M, DIN, DH>;
+  extern __shared__ __align__(16) float smem[];
+  G g;
+  float *p = g.init(smem, gp);
+  float *scratch = p; p += 4 * kFastWarps;
+  float *vx = p;
+  if (threadIdx.x < DX) vx[threadIdx.x] = vxg[threadIdx.x];
+  __syncthreads();
+
+  const Chain ch = chains.c[blockIdx.y];
+  const int nl = blockIdx.x * kFastThreads + threadIdx.x;
+  const bool live = nl < D.n_local;
+  const int nr = live ? nl : 0;
+  const int b = (D.n_offset + nr) / D.S;
+  const float *ub = u + (size_t)b * D.T * DU;
+  const float *yb = y + (size_t)b * D.T * DY;
+  const size_t np = ws.npad;
+
+  float h[DH], ent = 0.f;
+  {
+    const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + ch.t_hi) * D.n_local + nr] : 0.f;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) h[j] = z;
+  }
+#pragma unroll 1
+  for (int t = ch.t_hi; t >= ch.t_lo; --t) {
+    compiler_fence();
+    float xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DH], fv[DH];
+#pragma unroll
+    for (int j = 0; j < DH; ++j) xin[j] = h[j];
+#pragma unroll
+    for (int j = 0; j < DU; ++j) xin[DH + j] = ub[t * DU + j];
+#pragma unroll
+    for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
+    const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
+    gp_forward_fast<M, DIN, DH>(g, xin, xt, k, a, fm, fv);
+    const bool write = writer_run(t, D.R) == ch.run;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) {
+      const float f = fv[j] + vx[j];
+      h[j] = fm[j] + h[j] + e * sqrtf(f);
+      if (write) ent += 0.5f * (kLog2PiE + logf(f));
+    }
+    if (live) {
+      float *Hp = ws.H + (((size_t)ch.run * D.T + t) * DH) * np + nl;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) Hp[j * np] = h[j];
+    }
+  }
+  const float v[1] = {live ? ent : 0.f};
+  cta_sum_store<1>(v, scratch, part_out + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
+}
+
+// =====================================================================================
+template <int DX, int DU, int DY, int M>
+__global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
+    Dims D, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ vyg, const float *__restrict__ u,
+    const float *__restrict__ y, const float *__restrict__ eps_f, Workspace ws, float *__restrict__ part_out) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  using G = GpF<M, DIN, DX>;
+  extern __shared__ __align__(16) float smem[];
+  G g;
+  float *p = g.init(smem, gp);
+  float *scratch = p; p += (DY + 1) * kFastWarps;
+  float *vx = p; p += 4 * ((DX + 3) / 4);
+  float *vy = p;
+  if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
+  __syncthreads();
+
+  const int nl = blockIdx.x * kFastThreads + threadIdx.x;
+  const bool live = nl < D.n_local;
+  const int nr = live ? nl : 0;
+  const int b = (D.n_offset + nr) / D.S;
+  const float *ub = u + (size_t)b * D.T * DU;
+  const float *yb = y + (size_t)b * D.T * DY;
+  const size_t np = ws.npad;
+
+  auto load_ytil = [&](int t, float(&yt)[DX]) {
+#pragma unroll
+    for (int j = 0; j < DY; ++j) yt[j] = yb[t * DY + j];
+    const float *Hp = ws.H + (((size_t)writer_run(t, D.R) * D.T + t) * DH) * np + nr;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) yt[DY + j] = Hp[j * np];
+  };
+
+  float x[DX], sse[DY + 1], kl = 0.f;
+#pragma unroll
+  for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
+  load_ytil(0, x);
+#pragma unroll 1
+  for (int t = 0; t < D.T; ++t) {
+    compiler_fence();
+    if (live) {
+      float *Xp = ws.X + ((size_t)t * DX) * np + nl;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) Xp[j * np] = x[j];
+#pragma unroll
+      for (int j = 0; j < DY; ++j) { const float d = yb[t * DY + j] - x[j]; sse[j] = fmaf(d, d, sse[j]); }
+    }
+    if (t == D.T - 1) break;
+    float xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DX], fv[DX], yt[DX], xn[DX];
+#pragma unroll
+    for (int j = 0; j < DX; ++j) xin[j] = x[j];
+#pragma unroll
+    for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
+    load_ytil(t + 1, yt);
+    const float e = eps_f[(size_t)t * D.n_local + nr];
+    gp_forward_fast<M, DIN, DX>(g, xin, xt, k, a, fm, fv);
+    const bool do_cond = D.condition || (t < D.R - 1);
+    fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, xn, kl);
+#pragma unroll
+    for (int j = 0; j < DX; ++j) x[j] = xn[j];
+  }
+  sse[DY] = kl;
+  if (!live) {
+#pragma unroll
+    for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
+  }
+  cta_sum_store<DY + 1>(sse, scratch, part_out + (size_t)blockIdx.x * (DY + 1));
+}
+
+// =====================================================================================
+// Reverse kernels: persistent CTAs; every WARP writes its own partial slot
+// [tile accumulators | L_j, sum w, sum G, var_x_bar, var_y_bar].
+// =====================================================================================
+template <int DX, int DU, int DY, int M>
+__global__ void __launch_bounds__(kFastThreads, 3) fw_reverse_fast_kernel(
+    Dims D, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ vyg, const float *__restrict__ u,
+    const float *__restrict__ y, const float *__restrict__ eps_f, float w_ll, float w_kl, Workspace ws,
+    float *__restrict__ part_out, int slot) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  using G = GpF<M, DIN, DX>;
+  using W = WarpAcc<M, DIN, DX>;
+  extern __shared__ __align__(16) float smem[];
+  G g;
+  float *p = g.init(smem, gp);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *stg = p + warp * W::FLOATS; p += kFastWarps * W::FLOATS;
+  float *vx = p; p += 4 * ((DX + 3) / 4);
+  float *vy = p;
+  if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
+  for (int i = lane; i < W::FLOATS; i += 32) stg[i] = 0.f;
+  __syncthreads();
+
+  W wacc;
+  wacc.init(lane);
+  float Lacc[DIN], sw = 0.f, sG = 0.f, vxacc[DX], vyacc[DX];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) Lacc[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < DX; ++j) { vxacc[j] = 0.f; vyacc[j] = 0.f; }
+
+  const int ntile = ceil_div(D.n_local, kFastThreads);
+  const size_t np = ws.npad;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int nl = tile * kFastThreads + threadIdx.x;
+    const bool live = nl < D.n_local;
+    const int nr = live ? nl : 0;
+    const int b = (D.n_offset + nr) / D.S;
+    const float *ub = u + (size_t)b * D.T * DU;
+    const float *yb = y + (size_t)b * D.T * DY;
+
+    float xb[DX];
+    {
+      const float *Xp = ws.X + ((size_t)(D.T - 1) * DX) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DX; ++j)
+        xb[j] = (j < DY && live) ? w_ll * (yb[(D.T - 1) * DY + (j < DY ? j : 0)] - Xp[j * np]) / vy[j] : 0.f;
+    }
+#pragma unroll 1
+    for (int t = D.T - 2; t >= 0; --t) {
+    compiler_fence();
+      float x[DX], xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DX], fv[DX], yt[DX];
+      const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) { x[j] = Xp[j * np]; xin[j] = x[j]; }
+#pragma unroll
+      for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
+#pragma unroll
+      for (int j = 0; j < DY; ++j) yt[j] = yb[(t + 1) * DY + j];
+      {
+        const float *Hp = ws.H + (((size_t)writer_run(t + 1, D.R) * D.T + (t + 1)) * DH) * np + nr;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) yt[DY + j] = Hp[j * np];
+      }
+      const float e = eps_f[(size_t)t * D.n_local + nr];
+      gp_forward_fast<M, DIN, DX>(g, xin, xt, k, a, fm, fv);
+      const bool do_cond = D.condition || (t < D.R - 1);
+      float fmb[DX], fvb[DX], ytb[DX];
+      fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
+      if (live) {
+        float *Yp = ws.Yb + ((size_t)(t + 1) * DH) * np + nl;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) Yp[j * np] = ytb[DY + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < DX; ++j) { fmb[j] = 0.f; fvb[j] = 0.f; }
+      }
+      float xinb[DX];
+      __syncwarp();   // previous step's accumulate() has finished reading the staging tile
+      gp_reverse_fast<M, DIN, DX, DX>(g, stg, lane, xt, k, a, fmb, fvb, live, xinb, Lacc, sw, sG);
+      __syncwarp();
+      wacc.accumulate(stg);
+#pragma unroll
+      for (int j = 0; j < DX; ++j) {
+        float lg = 0.f;
+        if (j < DY && live) lg = w_ll * (yb[t * DY + (j < DY ? j : 0)] - x[j]) / vy[j];
+        xb[j] = xinb[j] + fmb[j] + lg;
+      }
+    }
+    if (live) {
+      float *Yp = ws.Yb + nl;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) Yp[j * np] = xb[DY + j];
+    }
+  }
+  // ---- per-warp partial ----
+  float *out = part_out + ((size_t)blockIdx.x * kFastWarps + warp) * slot;
+  wacc.store(out, lane);
+  float sc[DIN + 2 + 2 * DX];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) sc[j] = Lacc[j];
+  sc[DIN] = sw; sc[DIN + 1] = sG;
+#pragma unroll
+  for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = vxacc[j]; sc[DIN + 2 + DX + j] = vyacc[j]; }
+  float *so = out + round_up(W::NACC, 4);
+#pragma unroll
+  for (int i = 0; i < DIN + 2 + 2 * DX; ++i) {
+    float v = sc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) so[i] = v;
+  }
+}
+
+template <int DX, int DU, int DY, int M>
+__global__ void __launch_bounds__(kFastThreads, 3) bm_reverse_fast_kernel(
+    Dims D, ChainTable chains, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ u,
+    const float *__restrict__ y, const float *__restrict__ eps_b, const float *__restrict__ z_b, float w_en,
+    Workspace ws, float *__restrict__ part_out, int slot) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  using G = GpF<M, DIN, DH>;
+  using W = WarpAcc<M, DIN, DH>;
+  extern __shared__ __align__(16) float smem[];
+  G g;
+  float *p = g.init(smem, gp);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *stg = p + warp * W::FLOATS; p += kFastWarps * W::FLOATS;
+  float *vx = p;
+  if (threadIdx.x < DX) vx[threadIdx.x] = vxg[threadIdx.x];
+  for (int i = lane; i < W::FLOATS; i += 32) stg[i] = 0.f;
+  __syncthreads();
+
+  W wacc;
+  wacc.init(lane);
+  float Lacc[DIN], sw = 0.f, sG = 0.f, vxacc[DH];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) Lacc[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < DH; ++j) vxacc[j] = 0.f;
+
+  const int ntile = ceil_div(D.n_local, kFastThreads);
+  const int nitem = ntile * chains.count;
+  const size_t np = ws.npad;
+  for (int item = blockIdx.x; item < nitem; item += gridDim.x) {
+    const int tile = item % ntile;
+    const Chain ch = chains.c[item / ntile];
+    const int nl = tile * kFastThreads + threadIdx.x;
+    const bool live = nl < D.n_local;
+    const int nr = live ? nl : 0;
+    const int b = (D.n_offset + nr) / D.S;
+    const float *ub = u + (size_t)b * D.T * DU;
+    const float *yb = y + (size_t)b * D.T * DY;
+
+    float hb[DH];
+#pragma unroll
+    for (int j = 0; j < DH; ++j) hb[j] = 0.f;
+#pragma unroll 1
+    for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
+    compiler_fence();
+      float hid[DH], xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DH], fv[DH];
+      if (t == ch.t_hi) {
+        const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) hid[j] = z;
+      } else {
+        const float *Hp = ws.H + (((size_t)ch.run * D.T + (t + 1)) * DH) * np + nr;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) hid[j] = Hp[j * np];
+      }
+#pragma unroll
+      for (int j = 0; j < DH; ++j) xin[j] = hid[j];
+#pragma unroll
+      for (int j = 0; j < DU; ++j) xin[DH + j] = ub[t * DU + j];
+#pragma unroll
+      for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
+      const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
+      gp_forward_fast<M, DIN, DH>(g, xin, xt, k, a, fm, fv);
+      const bool write = writer_run(t, D.R) == ch.run;
+      float ob[DH], fvb[DH];
+      const float *Yp = ws.Yb + ((size_t)t * DH) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) {
+        const float f = fv[j] + vx[j];
+        float o = hb[j], fb = 0.f;
+        if (write) {
+          o += Yp[j * np];
+          fb = w_en * 0.5f / f;
+        }
+        fb += o * e * 0.5f * rsqrtf(f);
+        if (!live) { o = 0.f; fb = 0.f; }
+        ob[j] = o; fvb[j] = fb;
+        vxacc[j] += fb;
+      }
+      float xinb[DH];
+      __syncwarp();
+      gp_reverse_fast<M, DIN, DH, DH>(g, stg, lane, xt, k, a, ob, fvb, live, xinb, Lacc, sw, sG);
+      __syncwarp();
+      wacc.accumulate(stg);
+#pragma unroll
+      for (int j = 0; j < DH; ++j) hb[j] = xinb[j] + ob[j];
+    }
+  }
+  float *out = part_out + ((size_t)blockIdx.x * kFastWarps + warp) * slot;
+  wacc.store(out, lane);
+  float sc[DIN + 2 + 2 * DX];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) sc[j] = Lacc[j];
+  sc[DIN] = sw; sc[DIN + 1] = sG;
+#pragma unroll
+  for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = (j < DH) ? vxacc[j < DH ? j : 0] : 0.f; sc[DIN + 2 + DX + j] = 0.f; }
+  float *so = out + round_up(W::NACC, 4);
+#pragma unroll
+  for (int i = 0; i < DIN + 2 + 2 * DX; ++i) {
+    float v = sc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) so[i] = v;
+  }
+}
+
+}  // namespace cbf

@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(256) bm_forward_kernel(Dims D, ChainTable chai
 #pragma unroll
     for (int j = 0; j < DH; ++j) h[j] = z;
   }
+#pragma unroll 1
   for (int t = ch.t_hi; t >= ch.t_lo; --t) {
     float xin[DIN], xt[GpS<DIN, DH>::DINP], fm[DH], fv[DH];
 #pragma unroll
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(256) fw_forward_kernel(Dims D, GpDev gp, const
   for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
   float kl = 0.f;
   load_ytil(0, x);                                       // x_0 = y_tilde[:, 0]  (cbfssm.py:168)
+#pragma unroll 1
   for (int t = 0; t < D.T; ++t) {
     if (part == 0 && live) {
       float *Xp = ws.X + ((size_t)t * DX) * np + nl;
@@ -520,6 +522,7 @@ __global__ void __launch_bounds__(256) fw_reverse_kernel(Dims D, GpDev gp, const
       for (int j = 0; j < DX; ++j)
         xb[j] = (j < DY && live) ? w_ll * (yb[(D.T - 1) * DY + (j < DY ? j : 0)] - Xp[j * np]) / vy[j] : 0.f;
     }
+#pragma unroll 1
     for (int t = D.T - 2; t >= 0; --t) {
       float x[DX], xin[DIN], xt[GpS<DIN, DX>::DINP], fm[DX], fv[DX], yt[DX];
       const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(256) fw_reverse_kernel(Dims D, GpDev gp, const
   sc[DIN] = sw; sc[DIN + 1] = sG;
 #pragma unroll
   for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = vxacc[j]; sc[DIN + 2 + DX + j] = vyacc[j]; }
-  block_sum_store(sc, DIN + 2 + 2 * DX, red, out + L.nacc);
+  block_sum_store(sc, DIN + 2 + 2 * DX, red, out + L.scal_off());
 }
 
 // =====================================================================================
@@ -632,6 +635,7 @@ __global__ void __launch_bounds__(256) bm_reverse_kernel(Dims D, ChainTable chai
     float hb[DH];
 #pragma unroll
     for (int j = 0; j < DH; ++j) hb[j] = 0.f;
+#pragma unroll 1
     for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
       float hid[DH], xin[DIN], xt[GpS<DIN, DH>::DINP], fm[DH], fv[DH];
       if (t == ch.t_hi) {
@@ -683,7 +687,7 @@ __global__ void __launch_bounds__(256) bm_reverse_kernel(Dims D, ChainTable chai
   sc[DIN] = sw; sc[DIN + 1] = sG;
 #pragma unroll
   for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = vxacc[j]; sc[DIN + 2 + DX + j] = 0.f; }
-  block_sum_store(sc, DIN + 2 + 2 * DX, red, out + L.nacc);
+  block_sum_store(sc, DIN + 2 + 2 * DX, red, out + L.scal_off());
 }
 
 }  // namespace cbf

@@ -85,6 +85,11 @@ struct Launch {
     return cudaGetLastError();
   }
 
+  static void layouts(int M, AccLayout *Lf, AccLayout *Lb) {
+    *Lf = AccLayout(M, DIN, DX, DX);
+    *Lb = AccLayout(M, DIN, DH, DX);
+  }
+
   // Resident CTAs per SM of the two persistent reverse kernels (0 if they do not fit).
   static int occupancy(int M, int which) {
     const size_t smem = smem_bytes(M, which);
@@ -112,6 +117,10 @@ DimOps make_ops() {
   o.bm_reverse = &Launch<DX, DU, DY>::bm_reverse;
   o.smem_bytes = &Launch<DX, DU, DY>::smem_bytes;
   o.occupancy = &Launch<DX, DU, DY>::occupancy;
+  o.layouts = &Launch<DX, DU, DY>::layouts;
+  o.slots_per_cta = 1;
+  o.particles_per_cta = kNP;
+  o.fixed_M = 0;
   return o;
 }
 

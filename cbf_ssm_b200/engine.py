@@ -154,6 +154,7 @@ class ElboEngine:
         self._gflat = None
         self._shape = None
         self._saved = None
+        self.flags = 0             # CBF_FLAG_* passed in cbf_shape.flags
         self.launches = 0          # kernels of this library launched so far (bench.py gpu_launches)
 
     # ---------------- parameters ----------------
@@ -180,7 +181,7 @@ class ElboEngine:
         d = self.dims
         n_local = B * d.samples - n_offset if n_local is None else n_local
         return cbf_shape(B, d.samples, T, d.ind_pnt_num, d.dim_x, d.dim_u, d.dim_y, d.recog_len,
-                         1 if condition else 0, n_offset, n_local, float(d.k_factor))
+                         1 if condition else 0, n_offset, n_local, float(d.k_factor), int(self.flags))
 
     def _ensure_workspace(self, shape):
         key = (shape.B, shape.T, shape.n_local)

@@ -55,7 +55,12 @@ typedef struct cbf_shape {
   int32_t n_offset;   /* first global particle of this shard                        */
   int32_t n_local;    /* particles in this shard (B*S when unsharded)               */
   float   k_factor;   /* config['k_factor']                        cbfssm.py:191    */
+  int32_t flags;      /* CBF_FLAG_* (0 = default kernel selection)                  */
 } cbf_shape;
+
+/* Use the cooperative shared-memory kernels even when a register-resident
+ * instantiation for this (dims, M) is compiled in (parity tests cover both). */
+#define CBF_FLAG_FORCE_COOPERATIVE 1
 
 /* Kernel-level operands of one sparse GP (gp_tf.py:103-130), float32, produced by
  * cbf_gp_prologue (or by the caller).  Dout = dx for gp_f, dx-dy for gp_b. */

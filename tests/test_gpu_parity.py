@@ -13,11 +13,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def run_engine(cfg, params, u, y, eps_b, z_b, eps_f, condition=True):
+def run_engine(cfg, params, u, y, eps_b, z_b, eps_f, condition=True, flags=0):
     from cbf_ssm_b200.engine import ElboEngine, ModelDims
     dims = ModelDims(cfg.dim_x, cfg.dim_u, cfg.dim_y, cfg.ind_pnt_num, cfg.samples, cfg.recog_len,
                      cfg.k_factor, tuple(cfg.loss_factors))
     eng = ElboEngine(dims)
+    eng.flags = flags
     eng.set_params({k: v.numpy() for k, v in params.items()})
     dev = eng.device
     B, T, _ = u.shape
@@ -43,15 +44,27 @@ CASES = [
     (2, 1, 1, 12, 40, 2, 20, 4, 1.0, (10.0, 1.0), True, True),
     (8, 1, 4, 16, 7, 2, 14, 16, 2.0, (10.0, 0.0), True, True),
     (16, 1, 8, 9, 6, 1, 8, 2, 1.0, (10.0, 0.3), True, True),
+    # shapes with a register-resident instantiation (csrc/dims_list.h CBF_FAST_LIST)
+    (3, 1, 1, 12, 37, 5, 13, 3, 3.0, (6.0, 1.0), True, True),
+    (4, 1, 1, 20, 50, 3, 30, 16, 10.0, (10.0, 0.0), True, False),
+    (2, 1, 1, 20, 33, 4, 21, 4, 1.0, (10.0, 1.0), False, True),
+    (8, 1, 4, 20, 7, 5, 14, 16, 2.0, (10.0, 0.0), True, True),
+    (16, 1, 8, 20, 6, 3, 8, 2, 1.0, (10.0, 0.3), True, True),
+    (13, 6, 7, 20, 40, 4, 12, 4, 1.0, (20.0, 0.2), True, False),
 ]
 
+# 0: default kernel selection (register-resident kernels when compiled in);
+# 1: CBF_FLAG_FORCE_COOPERATIVE (shared-memory cooperative kernels)
+PATHS = [0, 1]
 
+
+@pytest.mark.parametrize("flags", PATHS, ids=["default", "cooperative"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "dx%d_du%d_dy%d_M%d_S%d_B%d_T%d_R%d" % c[:8])
-def test_elbo_and_gradients_match_oracle(case):
+def test_elbo_and_gradients_match_oracle(case, flags):
     dx, du, dy, M, S, B, T, R, kap, lf, cond, strong = case
     cfg, params, u, y, eps_b, z_b, eps_f = make_problem(dx, du, dy, M, S, B, T, R, kap, lf, seed=7, strong=strong)
     res, gd = O.loss_and_grads(cfg, params, u, y, eps_b, z_b, eps_f, cond)
-    eng, out, yd = run_engine(cfg, params, u, y, eps_b, z_b, eps_f, cond)
+    eng, out, yd = run_engine(cfg, params, u, y, eps_b, z_b, eps_f, cond, flags)
 
     for k in ("loss", "loglik", "kl_x", "entropy", "kl_z_f", "kl_z_b"):
         ref = float(getattr(res, k).detach())
@@ -76,11 +89,12 @@ def test_elbo_and_gradients_match_oracle(case):
     assert not bad, bad
 
 
-def test_kernel_level_gradients_match_kernel_math():
+@pytest.mark.parametrize("flags", PATHS, ids=["default", "cooperative"])
+def test_kernel_level_gradients_match_kernel_math(flags):
     cfg, params, u, y, eps_b, z_b, eps_f = make_problem(4, 2, 2, 7, 3, 2, 11, 3, 1.0, (10.0, 0.5), seed=3, strong=True)
     pn = {k: v.numpy() for k, v in params.items()}
     out, _ = KM.elbo_value_and_grad(cfg, pn, u, y, eps_b, z_b, eps_f, True)
-    eng, _, _ = run_engine(cfg, params, u, y, eps_b, z_b, eps_f, True)
+    eng, _, _ = run_engine(cfg, params, u, y, eps_b, z_b, eps_f, True, flags)
     kg = eng.kernel_level_grads()
     ref = out["kernel_level"]
     for tag in ("f", "b"):
