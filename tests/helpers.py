@@ -32,3 +32,32 @@ def rel_inf(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+# Named configurations of SURVEY.md 8(d) at the reference's own batch sizes
+# (cfg4 / cfg5 with the particle count reduced so the oracle finishes in seconds).
+NAMED_CASES = {
+    # name: dims, M, S, B, T, R, kap, lf, seed, config overrides
+    "cfg1_spring_template": dict(dx=4, du=1, dy=1, M=100, S=50, B=32, T=100, R=50, kap=1.0, lf=(10.0, 0.0), seed=0,
+                                 over=dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0)),
+    "cfg2_robomove_m20": dict(dx=4, du=2, dy=2, M=20, S=50, B=32, T=300, R=50, kap=1.0, lf=(20.0, 0.0), seed=1,
+                              over=dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0)),
+    "cfg3_sarcos": dict(dx=14, du=7, dy=7, M=100, S=20, B=5, T=250, R=16, kap=50.0, lf=(6.0, 0.0), seed=2,
+                        over=dict(zeta_pos=2.0, zeta_mean=0.0025, zeta_var=1e-4, gp_var=0.25, gp_len=1.0,
+                                  var_x=np.full(14, 4e-6), var_y=np.full(14, 0.0025))),
+    "cfg4_voliro_shaped": dict(dx=13, du=6, dy=7, M=20, S=64, B=4, T=64, R=16, kap=1.0, lf=(20.0, 0.0), seed=3,
+                               over=dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.25, gp_len=5.0,
+                                         var_x=np.full(13, 0.02 ** 2), var_y=np.full(13, 0.05 ** 2))),
+    "cfg5_sweep_d8_m100": dict(dx=8, du=1, dy=4, M=100, S=16, B=4, T=60, R=16, kap=1.0, lf=(10.0, 0.0), seed=4,
+                               over=dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0)),
+    "cfg2_predict_free_run": dict(dx=4, du=2, dy=2, M=20, S=50, B=2, T=120, R=50, kap=1.0, lf=(20.0, 0.0), seed=5,
+                                  cond=False,
+                                  over=dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0)),
+}
+
+
+def named_case(name):
+    c = NAMED_CASES[name]
+    cfg, params, u, y, eps_b, z_b, eps_f = make_problem(c["dx"], c["du"], c["dy"], c["M"], c["S"], c["B"], c["T"],
+                                                        c["R"], c["kap"], c["lf"], seed=c["seed"], **c["over"])
+    return cfg, params, u, y, eps_b, z_b, eps_f, c.get("cond", True)

@@ -1,0 +1,187 @@
+"""Size-independent properties, edge cases and the callers either side of the hot path,
+on the GPU through the C ABI / the reference-shaped Python interface."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cbfssm_oracle as O
+from tests.helpers import make_problem, rel_inf
+from tests.test_gpu_parity import run_engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(dx=4, du=2, dy=2, M=20, S=50, R=50, kap=1.0, lf=(20.0, 0.0), seed=1):
+    from cbf_ssm_b200.engine import ElboEngine, ModelDims, init_param_arrays
+    dims = ModelDims(dx, du, dy, M, S, R, kap, lf)
+    eng = ElboEngine(dims)
+    cfg = dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0,
+               var_x=np.full(dx, 0.01), var_y=np.full(dx, 1.0))
+    eng.set_params(init_param_arrays(dims, cfg, seed))
+    return eng
+
+
+def _inputs(eng, B, T, seed=0):
+    d, dev = eng.dims, eng.device
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    u = torch.randn(B, T, d.dim_u, generator=g).to(dev)
+    y = torch.randn(B, T, d.dim_y, generator=g).to(dev)
+    N = B * d.samples
+    eb = torch.randn(2, T, N, generator=g).to(dev)
+    zb = torch.randn(2, T, N, generator=g).to(dev)
+    ef = torch.randn(max(T - 1, 1), N, generator=g).to(dev)
+    return u, y, eb, zb, ef
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["default", "cooperative"])
+def test_sum_of_particle_shards_equals_the_whole_at_bench_shape(flags):
+    """Data-parallel contract at the BASELINE shape (M=20, T=300, S=50): the
+    kernel-level gradient and the ELBO terms of contiguous particle shards add up to the
+    unsharded result (fp32 summation-order tolerance); also bit-exact determinism."""
+    eng = _engine()
+    eng.flags = flags
+    B, T = 64, 300
+    u, y, eb, zb, ef = _inputs(eng, B, T)
+    N = B * eng.dims.samples
+    eng.forward(u, y, eb, zb, ef, True)
+    eng.backward()
+    whole_terms = eng.terms[:3].clone()
+    whole = eng._gflat.clone()
+    eng.forward(u, y, eb, zb, ef, True)
+    eng.backward()
+    assert torch.equal(whole, eng._gflat) and torch.equal(whole_terms, eng.terms[:3])   # deterministic reductions
+    acc = torch.zeros_like(whole)
+    tacc = torch.zeros_like(whole_terms)
+    bounds = [0, 1000, 1031, 2400, N]          # ragged shards, not multiples of 32 / 128 / S
+    for n0, n1 in zip(bounds[:-1], bounds[1:]):
+        sl = slice(n0, n1)
+        eng.forward(u, y, eb[:, :, sl].contiguous(), zb[:, :, sl].contiguous(), ef[:, sl].contiguous(), True,
+                    n_offset=n0, n_local=n1 - n0)
+        eng.backward()
+        acc += eng._gflat
+        tacc += eng.terms[:3]
+    torch.cuda.synchronize()
+    gl = eng._gl.total
+    assert rel_inf(tacc.cpu().numpy(), whole_terms.cpu().numpy()) < 1e-6
+    assert rel_inf(acc[:gl].cpu().numpy(), whole[:gl].cpu().numpy()) < 2e-5
+
+
+def test_loss_is_linear_in_the_loss_factors():
+    """loss = -(l1/S)(loglik - kl_x) - (l2/S) entropy + kl_z  (cbfssm.py:257-262)."""
+    e1 = _engine(lf=(20.0, 0.0))
+    u, y, eb, zb, ef = _inputs(e1, 8, 60)
+    o1 = {k: float(v) for k, v in e1.forward(u, y, eb, zb, ef, True).items()}
+    e2 = _engine(lf=(5.0, 3.0))
+    o2 = {k: float(v) for k, v in e2.forward(u, y, eb, zb, ef, True).items()}
+    for k in ("loglik", "kl_x", "entropy", "kl_z_f", "kl_z_b"):
+        assert o1[k] == o2[k]
+    S = 50.0
+    assert o2["loss"] == pytest.approx(-(5 / S) * (o2["loglik"] - o2["kl_x"]) - (3 / S) * o2["entropy"]
+                                       + o2["kl_z_f"] + o2["kl_z_b"], rel=1e-12)
+
+
+EDGE = [
+    # dx du dy  M  S  B  T   R   cond    what
+    (4, 2, 2, 20, 1, 1, 2, 50, True),      # single particle, two steps, T < R
+    (4, 2, 2, 20, 3, 1, 1, 4, True),       # T = 1: no forward step, no eps_f
+    (4, 2, 2, 20, 33, 1, 17, 1, True),     # R = 1: resample every second step
+    (4, 2, 2, 20, 129, 1, 9, 4, False),    # 129 particles: one past a CTA tile
+    (4, 1, 1, 100, 5, 3, 8, 8, True),      # T == R
+    (3, 1, 1, 12, 31, 1, 16, 8, False),    # T == 2R, free-running prediction after R-1 steps
+]
+
+
+@pytest.mark.parametrize("case", EDGE, ids=lambda c: "M%d_S%d_B%d_T%d_R%d_c%d" % (c[3], c[4], c[5], c[6], c[7], c[8]))
+def test_edge_shapes_match_oracle(case):
+    dx, du, dy, M, S, B, T, R, cond = case
+    cfg, params, u, y, eb, zb, ef = make_problem(dx, du, dy, M, S, B, T, R, 1.0, (10.0, 0.5), seed=21, strong=True)
+    res, gd = O.loss_and_grads(cfg, params, u, y, eb, zb, ef, cond)
+    eng, out, _ = run_engine(cfg, params, u, y, eb, zb, ef, cond)
+    assert float(out["loss"]) == pytest.approx(float(res.loss.detach()), rel=1e-4)
+    grads = eng.get_grads()
+    bad = {k: rel_inf(grads[k], gd[k].numpy()) for k in O.PARAM_NAMES}
+    bad = {k: v for k, v in bad.items() if not v < 1e-4 and np.max(np.abs(gd[k].numpy())) > 0}
+    assert not bad, bad
+
+
+def test_unsupported_shapes_fail_loudly():
+    from cbf_ssm_b200._lib import CbfError
+    from cbf_ssm_b200.engine import ElboEngine, ModelDims
+    with pytest.raises(CbfError):
+        ElboEngine(ModelDims(5, 5, 2, 20, 5, 4))        # dims not compiled in
+    with pytest.raises(CbfError):
+        ElboEngine(ModelDims(4, 2, 2, 500, 5, 4))       # M = 500 does not fit one SM (round-1 limit)
+
+
+def test_adam_step_matches_tf_formula():
+    eng = _engine(M=7)
+    g = torch.Generator().manual_seed(3)
+    theta0 = eng.theta.cpu().clone()
+    m = torch.zeros_like(theta0)
+    v = torch.zeros_like(theta0)
+    ref = theta0.clone()
+    for step in (1, 2, 3):
+        grad = torch.randn(theta0.numel(), generator=g, dtype=torch.float64)
+        eng.grad.copy_(grad)
+        eng.adam_step(0.05)
+        ref, m, v = O.adam_step_tf(ref, grad, m, v, step, 0.05)
+    torch.cuda.synchronize()
+    assert torch.allclose(eng.theta.cpu(), ref, rtol=1e-13, atol=1e-15)
+
+
+def test_philox_normals_are_standard_and_reproducible():
+    eng = _engine(M=7)
+    a = torch.empty(1 << 20, device=eng.device)
+    b = torch.empty_like(a)
+    eng.fill_normal(a, 7, 0)
+    eng.fill_normal(b, 7, 0)
+    assert torch.equal(a, b)
+    eng.fill_normal(b, 7, 1)
+    assert not torch.equal(a, b)
+    x = a.double().cpu().numpy()
+    assert abs(x.mean()) < 5e-3 and abs(x.std() - 1) < 5e-3
+    assert abs(np.mean(x ** 3)) < 2e-2 and abs(np.mean(x ** 4) - 3) < 5e-2
+    assert abs(np.corrcoef(x, b.double().cpu().numpy())[0, 1]) < 5e-3
+    c = torch.empty(1003, device=eng.device)            # ragged tail
+    eng.fill_normal(c, 7, 0)
+    assert torch.equal(c, a[:1003])
+
+
+def test_model_and_trainer_follow_the_reference_interface(tmp_path):
+    """run/template.py flow on a tiny problem: CBFSSM(config), Trainer.train(ds, epochs),
+    retrain from model.ckpt, prediction handles with condition=False."""
+    from cbf_ssm_b200.datasets import SpringNonlinearSynthetic
+    from cbf_ssm_b200.model import CBFSSM, Session
+    from cbf_ssm_b200.training import Trainer
+
+    class SmallSpring(SpringNonlinearSynthetic):
+        exp_len = 600
+    ds = SmallSpring(40, 20, seed=0)
+    dim_x = 4
+    config = {'ds': SmallSpring, 'batch_size': 8, 'shuffle': 10000, 'dim_x': dim_x, 'ind_pnt_num': 20, 'samples': 16,
+              'learning_rate': 0.01, 'loss_factors': np.asarray([10., 0.]), 'k_factor': 1., 'recog_len': 10,
+              'zeta_pos': 2., 'zeta_mean': 0.1 ** 2, 'zeta_var': 0.01 ** 2, 'var_x': np.asarray([0.1 ** 2] * dim_x),
+              'var_y': np.asarray([1. ** 2] * dim_x), 'gp_var': 0.1 ** 2, 'gp_len': 1., 'shuffle_seed': 0}
+    model = CBFSSM(config, seed=0)
+    trainer = Trainer(model, str(tmp_path))
+    trainer.train(ds, 4, verbose=False)
+    assert len(trainer.train_all) == 4 and len(trainer.test_all) == 4
+    assert trainer.train_all[-1] < trainer.train_all[0]            # Adam on the ELBO makes progress
+    assert os.path.exists(tmp_path / "best.ckpt") and os.path.exists(tmp_path / "model.ckpt")
+    theta = model.engine.theta.clone()
+    step = model.engine.adam_t
+    trainer.train(ds, 1, retrain=True, verbose=False)              # curriculum restart (run_robomove.py:47)
+    assert model.engine.adam_t > step and not torch.equal(theta, model.engine.theta)
+    # prediction path of cbfssm/outputs/outputs.py:68-71
+    sess = Session(model)
+    model.load_ds(sess, ds.test_in_batch[:1], ds.test_out_batch[:1])
+    pm, pv = sess.run((model.pred_mean, model.pred_var), {model.condition: False})
+    assert pm.shape == (1, 40, 1) and pv.shape == (1, 40, 1) and np.all(pv > 0)
+    noise = sess.run(model.var_dict['observation noise'])
+    assert noise.shape == (dim_x,) and np.all(noise > 0)
+    model.load_ds(sess, ds.test_in_batch, ds.test_out_batch)
+    losses = model.run(sess, model.loss, {model.condition: True})
+    assert losses[0].shape == (-(-ds.test_in_batch.shape[0] // 8),)   # list of per-fetch arrays (base_model.py:54)

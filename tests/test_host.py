@@ -1,0 +1,160 @@
+"""CPU tests of the host side: C-ABI surface, dataset windows, minibatch iterator."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import kernel_math as KM
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cbf_ssm_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from cbf_ssm_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "cbfssm_b200.h")).read()
+    declared = set(re.findall(r"CBF_API\s+[\w\s\*]+?\b(cbf_\w+)\s*\(", header))
+    assert len(declared) >= 18
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.cbf_abi_version() == 1
+
+
+def _shape(**kw):
+    from cbf_ssm_b200._lib import cbf_shape
+    d = dict(B=4, S=10, T=30, M=20, dx=4, du=2, dy=2, R=8, condition=1, n_offset=0, n_local=40, k_factor=1.0, flags=0)
+    d.update(kw)
+    return cbf_shape(*(d[f] for f, _ in cbf_shape._fields_))
+
+
+def test_host_only_entry_points_without_gpu(lib):
+    from cbf_ssm_b200._lib import cbf_grad_layout
+    assert lib.cbf_supported(20, 4, 2, 2) == 1
+    assert lib.cbf_supported(100, 4, 1, 1) == 1
+    assert lib.cbf_supported(100, 14, 7, 7) == 1
+    assert lib.cbf_supported(20, 5, 5, 5) == 0          # dims not compiled in
+    assert lib.cbf_supported(500, 4, 2, 2) == 0         # resident set exceeds one SM
+    n = C.c_size_t(0)
+    s = _shape()
+    assert lib.cbf_workspace_bytes(C.byref(s), C.byref(n)) == 0 and n.value > 0
+    gl = cbf_grad_layout()
+    assert lib.cbf_grad_layout_get(C.byref(s), C.byref(gl)) == 0
+    M, din, dx, dh = 20, 6, 4, 2
+    assert gl.total == 2 * (M * M + M * din + din + 1) + 2 * M * dx + 2 * M * dh + 2 * dx
+    assert lib.cbf_gp_prologue_state_doubles(20, 6, 4) > 2 * 400
+
+
+@pytest.mark.parametrize("bad", [dict(T=0), dict(dy=4), dict(n_local=41), dict(R=0), dict(M=0), dict(n_offset=-1)])
+def test_invalid_shapes_are_rejected(lib, bad):
+    n = C.c_size_t(0)
+    s = _shape(**bad)
+    assert lib.cbf_workspace_bytes(C.byref(s), C.byref(n)) == -1
+    assert b"invalid shape" in lib.cbf_last_error_string()
+
+
+def test_null_arguments_are_rejected(lib):
+    assert lib.cbf_workspace_bytes(None, None) == -5
+    assert lib.cbf_adam_step(4, None, None, None, None, 1, 0.01, 0.9, 0.999, 1e-8, None) == -5
+
+
+def test_missing_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from cbf_ssm_b200.engine import ElboEngine, ModelDims
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ElboEngine(ModelDims(4, 2, 2, 20, 5, 4))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "cbf_ssm_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+@pytest.mark.parametrize("T,R", [(100, 50), (300, 50), (250, 16), (6, 50), (5000, 16), (33, 1)])
+def test_chain_launch_count_matches_chain_table(T, R):
+    from cbf_ssm_b200.engine import count_chain_batches
+    n = len(KM.build_chains(T, R))
+    assert count_chain_batches(T, R) == (0 if n == 0 else -(-n // 120))
+
+
+def test_window_counts_of_the_named_datasets():
+    """base_ds.py:54-77 semantics; counts cross-checked against the reference in SURVEY 8c."""
+    from cbf_ssm_b200.datasets import BaseDS
+    x = np.arange(5000 * 1, dtype=float).reshape(1, 5000, 1)
+    assert BaseDS.rnn_batches(x, 100, 50).shape == (99, 100, 1)           # SpringNonlinear
+    x = np.zeros((1, 25000, 2))
+    assert BaseDS.rnn_batches(x, 300, 50).shape[0] == 495                 # RoboMove
+    x = np.zeros((60, 337, 7))
+    assert BaseDS.rnn_batches(x, 250, 10).shape[0] == 600                 # Sarcos
+    # the remainder window holds the last samples
+    x = np.arange(23, dtype=float).reshape(1, 23, 1)
+    w = BaseDS.rnn_batches(x, 10, 4)
+    assert w.shape[0] == 5 and w[-1, -1, 0] == 22 and w[-2, 0, 0] == 12
+    with pytest.raises(AssertionError):
+        BaseDS.rnn_batches(np.zeros((1, 5, 1)), 10, 1)
+
+
+def test_normalisation_round_trip():
+    from cbf_ssm_b200.datasets import SpringNonlinearSynthetic
+    ds = SpringNonlinearSynthetic(100, 50, seed=0)
+    assert ds.train_in_batch.shape == (99, 100, 1) and ds.test_out_batch.shape == (99, 100, 1)
+    assert abs(ds.train_out.mean()) < 1e-9 and abs(ds.train_out.std() - 1) < 1e-9
+    z = ds.normalize(np.array([[0.3]]), 'out')
+    assert np.allclose(ds.denormalize(z, 'out'), 0.3)
+
+
+class _FakeModel:
+    """BaseModel with the device work replaced: returns the batch it was given."""
+
+    def __new__(cls, config):
+        from cbf_ssm_b200.model.base_model import BaseModel
+
+        class M(BaseModel):
+            def _build_graph(self):
+                self.loss = self._handle("loss")
+                self.idx = self._handle("idx")
+
+            def _session_run(self, fetches, feed_dict):
+                u, y = self._next_batch()
+                return (np.float64(u.sum()), u[:, 0, 0].copy())
+        return M(config)
+
+
+def test_load_ds_and_run_follow_the_reference_iterator_semantics():
+    from cbf_ssm_b200.model.base_model import Session
+
+    class DS:
+        dim_u, dim_y = 1, 1
+    n = 10
+    data = np.arange(n, dtype=float).reshape(n, 1, 1) * np.ones((1, 3, 1))
+    model = _FakeModel({"ds": DS, "batch_size": 4, "shuffle": 10000, "shuffle_seed": 0})
+    sess = Session(model)
+    model.load_ds(sess, data, data)
+    loss, idx = model.run(sess, (model.loss, model.idx), {model.condition: True})
+    assert loss.shape == (3,)                       # ceil(10/4) batches, scalars -> vector (base_model.py:57)
+    assert sorted(idx.tolist()) == list(range(n))   # every window exactly once, last batch short
+    assert idx.tolist() != list(range(n))           # shuffled
+    model.load_ds(sess, data, data, repeats=2)
+    _, idx2 = model.run(sess, (model.loss, model.idx), {})
+    assert sorted(idx2.tolist()) == sorted(list(range(n)) * 2)
+    model2 = _FakeModel({"ds": DS, "batch_size": 4, "shuffle": 1})
+    model2.load_ds(Session(model2), data, data)
+    _, idx3 = model2.run(Session(model2), (model2.loss, model2.idx), {})
+    assert idx3.tolist() == list(range(n))          # buffer of 1 = no shuffle
+    model3 = _FakeModel({"ds": DS, "batch_size": 4, "shuffle": 3, "shuffle_seed": 1})
+    model3.load_ds(Session(model3), data, data)
+    _, idx4 = model3.run(Session(model3), (model3.loss, model3.idx), {})
+    assert sorted(idx4.tolist()) == list(range(n))
+    assert all(v <= i + 2 for i, v in enumerate(idx4.tolist()))   # bounded look-ahead of a size-3 buffer

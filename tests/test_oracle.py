@@ -1,0 +1,150 @@
+"""CPU checks of the oracle itself (it cannot be compared with TensorFlow here, so it is
+validated by identities, finite differences, a second restatement and golden files)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cbfssm_oracle as O
+from oracle import kernel_math as KM
+from tests.helpers import NAMED_CASES, make_problem, named_case, rel_inf
+
+
+def test_positive_transform_round_trip_and_guards():
+    y = np.array([1e-9, 1e-4, 0.3, 1.0, 20.0, 36.0, 50.0])
+    x = O.positive_backward(y)
+    back = O.positive_forward(torch.tensor(x)).numpy()
+    assert np.allclose(back, y, rtol=1e-9, atol=1e-12)
+    assert x[-1] == pytest.approx(50.0 - 1e-10)          # y > 35 branch (tf_transform.py:16)
+    with pytest.raises(AssertionError):
+        O.positive_backward(np.array([1e-10]))
+
+
+def test_rbf_matches_brute_force():
+    g = np.random.default_rng(0)
+    X, Z = g.standard_normal((7, 3)), g.standard_normal((5, 3))
+    ell, var = np.array([0.5, 1.3, 2.0]), 0.7
+    kern = O.RBF(torch.tensor(O.positive_backward(var)), torch.tensor(O.positive_backward(ell)))
+    K = kern.K(torch.tensor(Z), torch.tensor(X)).numpy()
+    ref = np.array([[var * math.exp(-0.5 * np.sum(((z - x) / ell) ** 2)) for x in X] for z in Z])
+    assert np.allclose(K, ref, rtol=1e-12)
+    assert np.allclose(kern.Kdiag(torch.tensor(X)).numpy(), var)
+
+
+def _small_gp(seed=0, M=6, din=3, dout=2):
+    g = np.random.default_rng(seed)
+    Z = torch.tensor(g.uniform(-2, 2, (M, din)))
+    m = torch.tensor(g.standard_normal((M, dout)))
+    Su = torch.tensor(O.positive_backward(g.uniform(0.01, 0.3, (M, dout))))
+    gp = O.GPModel(Z, m, Su, torch.tensor(O.positive_backward(0.8)), torch.tensor(O.positive_backward(np.full(din, 1.1))))
+    return gp, g
+
+
+def test_predict_matches_dense_gp_formulas():
+    gp, g = _small_gp()
+    X = torch.tensor(g.standard_normal((9, 3)))
+    fm, fv = gp.predict(X)
+    Kzz = gp.kern.K(gp.zeta_pos).numpy() + 1e-8 * np.eye(6)
+    Kzx = gp.kern.K(gp.zeta_pos, X).numpy()
+    A = np.linalg.solve(Kzz, Kzx)                                    # [M, N]
+    assert np.allclose(fm.numpy(), A.T @ gp.zeta_mean.numpy(), rtol=1e-9)
+    base = float(gp.kern.variance) - np.sum(Kzx * A, axis=0)
+    ref = base[:, None] + (A ** 2).T @ gp.zeta_var.numpy()
+    assert np.allclose(fv.numpy(), ref, rtol=1e-8)
+
+
+def test_prior_kl_matches_torch_distributions():
+    gp, _ = _small_gp(1)
+    total = 0.0
+    for d in range(gp.out_dim):
+        q = torch.distributions.MultivariateNormal(gp.zeta_mean[:, d], covariance_matrix=torch.diag(gp.zeta_var[:, d]))
+        p = torch.distributions.MultivariateNormal(torch.zeros(6, dtype=O.DT), scale_tril=gp.cholesky)
+        total += float(torch.distributions.kl_divergence(q, p))
+    assert float(gp.prior_kl()) == pytest.approx(total, rel=1e-10)
+
+
+@pytest.mark.parametrize("T,R,live", [(100, 50, 150), (300, 50, 550), (250, 16, 484), (50, 16, 84), (64, 16, 112),
+                                      (500, 16, 984), (500, 50, 950)])
+def test_schedule_and_live_steps(T, R, live):
+    """Literal flags of cbfssm.py:123-128; every t written exactly once; the chain table
+    drops exactly the dead tail (SURVEY 8a note 5 table)."""
+    writes = np.zeros(T, int)
+    for run in (0, 1):
+        for t in range(T):
+            rs, wr = O.backward_schedule(run, t, R)
+            assert rs == (((t + 1) if run == 0 else (t + R + 1)) % (2 * R) == 0)
+            writes[t] += wr
+    assert np.all(writes == 1)
+    chains = KM.build_chains(T, R)
+    assert sum(hi - lo + 1 for (_, hi, lo, _) in chains) == live
+    # brute-force liveness: a step is live iff some later (lower t) step of its segment is written
+    for run in (0, 1):
+        seg_live = set()
+        t = T - 1
+        while t >= 0:
+            seg = [t]
+            t -= 1
+            while t >= 0 and not O.backward_schedule(run, t, R)[0]:
+                seg.append(t)
+                t -= 1
+            written = [s for s in seg if O.backward_schedule(run, s, R)[1]]
+            if written:
+                seg_live.update(s for s in seg if s >= min(written))
+        table = set()
+        for (r, hi, lo, _) in chains:
+            if r == run:
+                table.update(range(lo, hi + 1))
+        assert table == seg_live
+
+
+def test_oracle_gradients_match_finite_differences():
+    cfg, params, u, y, eb, zb, ef = make_problem(3, 1, 1, 4, 2, 2, 7, 2, 3.0, (6.0, 1.0), seed=5, strong=True)
+    _, gd = O.loss_and_grads(cfg, params, u, y, eb, zb, ef, True)
+    rng = np.random.default_rng(0)
+    for name in O.PARAM_NAMES:
+        base = params[name]
+        flat = base.reshape(-1)
+        for idx in rng.choice(flat.numel(), size=min(3, flat.numel()), replace=False):
+            h = 1e-6
+            vals = []
+            for sgn in (+1, -1):
+                p2 = {k: v.clone() for k, v in params.items()}
+                p2[name].reshape(-1)[idx] += sgn * h
+                vals.append(float(O.elbo(cfg, p2, u, y, eb, zb, ef, True).loss))
+            fd = (vals[0] - vals[1]) / (2 * h)
+            an = float(gd[name].reshape(-1)[idx])
+            assert fd == pytest.approx(an, rel=2e-5, abs=1e-6), (name, idx)
+
+
+@pytest.mark.parametrize("cond", [True, False])
+def test_kernel_algebra_restatement_agrees(cond):
+    cfg, params, u, y, eb, zb, ef = make_problem(4, 2, 2, 7, 3, 2, 11, 3, 2.0, (10.0, 0.5), seed=2, strong=True)
+    res, gd = O.loss_and_grads(cfg, params, u, y, eb, zb, ef, cond)
+    out, g2 = KM.elbo_value_and_grad(cfg, {k: v.numpy() for k, v in params.items()}, u, y, eb, zb, ef, cond)
+    assert out["loss"] == pytest.approx(float(res.loss.detach()), rel=1e-12)
+    for k in O.PARAM_NAMES:
+        assert rel_inf(g2[k], gd[k].numpy()) < 1e-10, k
+
+
+def test_tf_adam_differs_from_torch_adam_only_in_epsilon_placement():
+    th = torch.tensor([0.3, -1.2], dtype=O.DT)
+    g = torch.tensor([0.5, -2.0], dtype=O.DT)
+    t1, m, v = O.adam_step_tf(th, g, torch.zeros(2, dtype=O.DT), torch.zeros(2, dtype=O.DT), 1, 0.01)
+    # first step: m_hat/sqrt(v_hat) = sign(g); TF: lr*sqrt(1-b2)/(1-b1) * m/(sqrt(v)+eps)
+    lr_t = 0.01 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    ref = th - lr_t * (0.1 * g) / (torch.sqrt(0.001 * g * g) + 1e-8)
+    assert torch.allclose(t1, ref, rtol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["cfg4_voliro_shaped", "cfg5_sweep_d8_m100", "cfg2_predict_free_run"])
+def test_oracle_reproduces_golden(name):
+    """The committed golden files are what the oracle produces (regression pin)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    cfg, params, u, y, eb, zb, ef, cond = named_case(name)
+    res, gd = O.loss_and_grads(cfg, params, u, y, eb, zb, ef, cond)
+    assert float(res.loss.detach()) == pytest.approx(float(gold["loss"]), rel=1e-10)
+    for k in O.PARAM_NAMES:
+        assert rel_inf(gd[k].numpy(), gold["grad." + k]) < 1e-8, k
+    assert rel_inf(res.pred_mean.detach().numpy(), gold["pred_mean"]) < 1e-10
