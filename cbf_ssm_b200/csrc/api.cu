@@ -100,7 +100,7 @@ struct Plan {
   int ptiles, slots_per_cta;
   std::vector<Chain> chains;
   AccLayout Lf, Lb;
-  size_t off_X, off_H, off_Yb, off_fbm, off_ffw, off_gf, off_gb, off_accf, off_accb, off_stats, total;
+  size_t off_X, off_H, off_Yb, off_fbm, off_ffw, off_gf, off_gb, off_accf, off_accb, off_stats, off_cpack, total;
   const DimOps *ops;
 };
 
@@ -155,6 +155,7 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   p.off_accf = o; o = align_up(o + sizeof(double) * p.Lf.slot(), 256);
   p.off_accb = o; o = align_up(o + sizeof(double) * p.Lb.slot(), 256);
   p.off_stats = o; o = align_up(o + sizeof(double) * (p.dy + 2), 256);
+  p.off_cpack = o; o = align_up(o + sizeof(float) * 2 * 2048, 256);
   p.total = o;
   return 0;
 }
@@ -172,6 +173,7 @@ static Workspace bind_workspace(const Plan &p, void *base) {
   w.acc_f = reinterpret_cast<double *>(b + p.off_accf);
   w.acc_b = reinterpret_cast<double *>(b + p.off_accb);
   w.stats = reinterpret_cast<double *>(b + p.off_stats);
+  w.cpack = reinterpret_cast<float *>(b + p.off_cpack);
   w.npad = p.D.npad;
   return w;
 }

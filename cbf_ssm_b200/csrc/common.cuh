@@ -44,6 +44,7 @@ struct Workspace {
   double *acc_f;   // [slot_f]           reduced
   double *acc_b;   // [slot_b]
   double *stats;   // sse[dy], kl_x, entropy of this shard (float64)
+  float *cpack;    // [2][2048] packed constant-bank images of the two GPs (register path)
   int npad;
 };
 

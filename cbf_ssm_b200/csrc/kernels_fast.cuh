@@ -47,17 +47,94 @@ constexpr TileCfg pick_tiles(int M, int Din, int Dout) {
   return best;
 }
 
+
+// ---- resident operands in the constant bank -------------------------------------------
+// Measured on B200 (profiles/r01b_fast_bm_reverse_full.txt + source page): a warp-uniform
+// LDS.128 costs 2 shared-memory wavefronts (8 useful bytes per wavefront), so streaming P, Z/ell,
+// alpha and S through broadcast shared loads made the register path shared-memory bound
+// (~77 % of shared-pipe cycles).  With CBF_CONST_OPERANDS the packed operands of the GP a
+// kernel uses live in a __constant__ array instead and every use is an FFMA/FADD with a
+// c[bank][imm] operand: no load instruction and no shared-memory traffic.  P is stored as its
+// upper triangle (it is symmetric) to keep the working set inside the 2 KB constant L1.
+// The array is per translation unit; it is refreshed before each launch by a device-to-device
+// cudaMemcpyToSymbolAsync on the caller's stream (see launch_fast.cuh), so calls of one
+// instantiation must not overlap on different streams.
+#ifndef CBF_CONST_OPERANDS
+#define CBF_CONST_OPERANDS 1
+#endif
+constexpr bool kConstOps = CBF_CONST_OPERANDS != 0;
+constexpr int kConstFloats = 2048;              // per GP slot (8 KB)
+static __constant__ float c_ops[2][kConstFloats];      // [0] forward-rollout GP, [1] backward-message GP
+
+template <int SLOT, int M, int DIN, int DOUT>
+struct CO {
+  static constexpr int oP = 0, oZ = M * (M + 1) / 2, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT;
+  static constexpr int oSig = oI + DIN, oLs = oSig + 1, TOTAL = oLs + 1;
+  static_assert(TOTAL <= kConstFloats, "operands exceed the constant slot");
+  static __device__ __forceinline__ float P(int m, int mp) {   // symmetric, upper triangle
+    const int a = m < mp ? m : mp, b = m < mp ? mp : m;
+    return c_ops[SLOT][oP + a * M - a * (a - 1) / 2 + (b - a)];
+  }
+  static __device__ __forceinline__ float Zt(int m, int j) { return c_ops[SLOT][oZ + m * DIN + j]; }
+  static __device__ __forceinline__ float al(int m, int d) { return c_ops[SLOT][oA + m * DOUT + d]; }
+  static __device__ __forceinline__ float S(int m, int d) { return c_ops[SLOT][oS + m * DOUT + d]; }
+  static __device__ __forceinline__ float il(int j) { return c_ops[SLOT][oI + j]; }
+  static __device__ __forceinline__ float sig2() { return c_ops[SLOT][oSig]; }
+  static __device__ __forceinline__ float lsig() { return c_ops[SLOT][oLs]; }
+};
+
+// Packs one GP's operands in the CO<> layout (runtime sizes) into global scratch.
+static __global__ void pack_const_kernel(GpDev g, int M, int DIN, int DOUT, float *__restrict__ out) {
+  const int oZ = M * (M + 1) / 2, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT, oSig = oI + DIN;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = tid; i < M * M; i += nt) {
+    const int a = i / M, b = i % M;
+    if (a <= b) out[a * M - a * (a - 1) / 2 + (b - a)] = 0.5f * (g.P[a * M + b] + g.P[b * M + a]);
+  }
+  for (int i = tid; i < M * DIN; i += nt) out[oZ + i] = g.Z[i] / g.ell[i % DIN];
+  for (int i = tid; i < M * DOUT; i += nt) { out[oA + i] = g.alpha[i]; out[oS + i] = g.S[i]; }
+  for (int i = tid; i < DIN; i += nt) out[oI + i] = 1.f / g.ell[i];
+  if (tid == 0) { out[oSig] = g.sig2[0]; out[oSig + 1] = log2f(g.sig2[0]); }
+}
+
+// a = P k with P from the constant bank (upper triangle, each off-diagonal value feeds two FMAs).
+template <int SLOT, int M, int DIN, int DOUT, int MP>
+__device__ __forceinline__ void matvec_const(const float (&k)[MP], float (&a)[MP]) {
+  using C = CO<SLOT, M, DIN, DOUT>;
+#pragma unroll
+  for (int m = 0; m < MP; ++m) a[m] = (m < M) ? C::P(m < M ? m : 0, m < M ? m : 0) * k[m] : 0.f;
+  // rectangular loops with a compile-time predicate: unrolls fully, the dead half folds away
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+#pragma unroll
+    for (int mp = 0; mp < M; ++mp) {
+      if (mp > m) {
+        const float p = C::P(m, mp);
+        a[m] = fmaf(p, k[mp], a[m]);
+        a[mp] = fmaf(p, k[m], a[mp]);
+      }
+    }
+  }
+}
+
 // Shared-memory image of one GP's operands, compile-time sizes.
-template <int M, int DIN, int DOUT>
+template <int M, int DIN, int DOUT, int SLOT>
 struct GpF {
   static constexpr int MP = (M + 3) / 4 * 4;
   static constexpr int DINP = (DIN + 3) / 4 * 4;
   static constexpr int DOUTP = (DOUT + 3) / 4 * 4;
-  static constexpr int FLOATS = MP * MP + MP * (DINP + 2 * DOUTP) + DINP + 4;
+  static constexpr int FLOATS = kConstOps ? 0 : MP * MP + MP * (DINP + 2 * DOUTP) + DINP + 4;
+  using C = CO<SLOT, M, DIN, DOUT>;
   const float *P, *Zt, *al, *Sm, *il;
   float sig2, lsig;
 
   __device__ float *init(float *base, const GpDev &g) {
+    if constexpr (kConstOps) {
+      P = Zt = al = Sm = il = nullptr;
+      sig2 = C::sig2();
+      lsig = C::lsig();
+      return base;
+    }
     float *Pw = base; base += MP * MP;
     float *Zw = base; base += MP * DINP;
     float *aw = base; base += MP * DOUTP;
@@ -118,13 +195,48 @@ __device__ __forceinline__ void matvec_fast(const float *__restrict__ P, const f
 }
 
 // One sparse-GP evaluation (gp_tf.py:132-161) for the thread's particle.
-template <int M, int DIN, int DOUT>
-__device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT> &g, const float (&xin)[DIN],
-                                                float (&xt)[GpF<M, DIN, DOUT>::DINP],
-                                                float (&k)[GpF<M, DIN, DOUT>::MP], float (&a)[GpF<M, DIN, DOUT>::MP],
-                                                float (&fm)[DOUT], float (&fv)[DOUT]) {
-  using G = GpF<M, DIN, DOUT>;
+template <int M, int DIN, int DOUT, int SLOT>
+__device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g, const float (&xin)[DIN],
+                                                float (&xt)[GpF<M, DIN, DOUT, SLOT>::DINP],
+                                                float (&k)[GpF<M, DIN, DOUT, SLOT>::MP],
+                                                float (&a)[GpF<M, DIN, DOUT, SLOT>::MP], float (&fm)[DOUT],
+                                                float (&fv)[DOUT]) {
+  using G = GpF<M, DIN, DOUT, SLOT>;
   constexpr int MP = G::MP, DINP = G::DINP, DOUTP = G::DOUTP;
+  if constexpr (kConstOps) {
+    using C = typename G::C;
+#pragma unroll
+    for (int j = 0; j < DINP; ++j) xt[j] = (j < DIN) ? xin[j < DIN ? j : 0] * C::il(j < DIN ? j : 0) : 0.f;
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) fm[d] = 0.f;
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      if (m < M) {
+        float d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < DIN; ++j) { const float e = xt[j] - C::Zt(m < M ? m : 0, j); d2 = fmaf(e, e, d2); }
+        k[m] = exp2f(fmaf(kNegHalfLog2e, d2, g.lsig));
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(k[m], C::al(m < M ? m : 0, d), fm[d]);
+      } else {
+        k[m] = 0.f;
+      }
+    }
+    matvec_const<SLOT, M, DIN, DOUT, MP>(k, a);
+    float q = 0.f;
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      q = fmaf(k[m], a[m], q);
+      const float a2 = a[m] * a[m];
+#pragma unroll
+      for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, C::S(m, d), fv[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) fv[d] = g.sig2 - q + fv[d];
+    return;
+  }
   {
     float il[DINP];
     ld_row<DINP>(g.il, il);
@@ -250,16 +362,70 @@ struct WarpAcc {
 
 // Reverse of one GP evaluation (SURVEY 8a note 4) for the thread's particle; stages the
 // outer-product operands into the warp tile.  k, a from gp_forward_fast.
-template <int M, int DIN, int DOUT, int NEED>
-__device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT> &g, float *__restrict__ stg, int lane,
-                                                const float (&xt)[GpF<M, DIN, DOUT>::DINP],
-                                                const float (&k)[GpF<M, DIN, DOUT>::MP],
-                                                const float (&a)[GpF<M, DIN, DOUT>::MP], const float (&gm)[DOUT],
-                                                const float (&gv)[DOUT], bool live, float (&xinb)[NEED],
-                                                float (&Lacc)[DIN], float &sw, float &sG) {
-  using G = GpF<M, DIN, DOUT>;
+template <int M, int DIN, int DOUT, int NEED, int SLOT>
+__device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g, float *__restrict__ stg, int lane,
+                                                const float (&xt)[GpF<M, DIN, DOUT, SLOT>::DINP],
+                                                const float (&k)[GpF<M, DIN, DOUT, SLOT>::MP],
+                                                const float (&a)[GpF<M, DIN, DOUT, SLOT>::MP],
+                                                const float (&gm)[DOUT], const float (&gv)[DOUT], bool live,
+                                                float (&xinb)[NEED], float (&Lacc)[DIN], float &sw, float &sG) {
+  using G = GpF<M, DIN, DOUT, SLOT>;
   using W = WarpAcc<M, DIN, DOUT>;
   constexpr int MP = G::MP, DINP = G::DINP, DOUTP = G::DOUTP;
+  if constexpr (kConstOps) {
+    using C = typename G::C;
+    float Gs = 0.f;
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) Gs += gv[d];
+    sG += Gs;
+    float b[MP];
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      if (m < M) {
+        float c = 0.f;
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) c = fmaf(C::S(m < M ? m : 0, d), gv[d], c);
+        b[m] = a[m] * c;
+      } else {
+        b[m] = 0.f;
+      }
+    }
+    float pb[MP];
+    matvec_const<SLOT, M, DIN, DOUT, MP>(b, pb);
+#pragma unroll
+    for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
+    float *sp = stg + lane;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float kb = 2.f * pb[m] - 2.f * Gs * a[m];
+#pragma unroll
+      for (int d = 0; d < DOUT; ++d) kb = fmaf(C::al(m, d), gm[d], kb);
+      const float w = kb * k[m];
+      sw += w;
+#pragma unroll
+      for (int j = 0; j < DIN; ++j) {
+        const float dl = xt[j] - C::Zt(m, j);
+        const float wd = w * dl;
+        if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
+        Lacc[j] = fmaf(wd, dl, Lacc[j]);
+      }
+      sp[(W::rowK + m) * kSLD] = k[m];
+      sp[(W::rowAb + m) * kSLD] = 2.f * b[m] - Gs * k[m];
+      sp[(W::rowAsq + m) * kSLD] = a[m] * a[m];
+      sp[(W::rowW + m) * kSLD] = w;
+    }
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) {
+      sp[(W::rowGm + d) * kSLD] = gm[d];
+      sp[(W::rowGv + d) * kSLD] = gv[d];
+    }
+#pragma unroll
+    for (int j = 0; j < DIN; ++j) sp[(W::rowX + j) * kSLD] = live ? xt[j] : 0.f;
+    sp[(W::rowX + DIN) * kSLD] = live ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < NEED; ++j) xinb[j] *= C::il(j);
+    return;
+  }
   float Gs = 0.f;
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) Gs += gv[d];
@@ -353,7 +519,7 @@ __global__ void __launch_bounds__(kFastThreads) bm_forward_fast_kernel(
     const float *__restrict__ y, const float *__restrict__ eps_b, const float *__restrict__ z_b, Workspace ws,
     float *__restrict__ part_out) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using G = GpF<M, DIN, DH>;
+  using G = GpF<M, DIN, DH, 1>;
   extern __shared__ __align__(16) float smem[];
   G g;
   float *p = g.init(smem, gp);
@@ -388,7 +554,7 @@ __global__ void __launch_bounds__(kFastThreads) bm_forward_fast_kernel(
 #pragma unroll
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
-    gp_forward_fast<M, DIN, DH>(g, xin, xt, k, a, fm, fv);
+    gp_forward_fast<M, DIN, DH, 1>(g, xin, xt, k, a, fm, fv);
     const bool write = writer_run(t, D.R) == ch.run;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
@@ -412,7 +578,7 @@ __global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
     Dims D, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ vyg, const float *__restrict__ u,
     const float *__restrict__ y, const float *__restrict__ eps_f, Workspace ws, float *__restrict__ part_out) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using G = GpF<M, DIN, DX>;
+  using G = GpF<M, DIN, DX, 0>;
   extern __shared__ __align__(16) float smem[];
   G g;
   float *p = g.init(smem, gp);
@@ -460,7 +626,7 @@ __global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
     for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
     load_ytil(t + 1, yt);
     const float e = eps_f[(size_t)t * D.n_local + nr];
-    gp_forward_fast<M, DIN, DX>(g, xin, xt, k, a, fm, fv);
+    gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
     const bool do_cond = D.condition || (t < D.R - 1);
     fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, xn, kl);
 #pragma unroll
@@ -484,7 +650,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fw_reverse_fast_kernel(
     const float *__restrict__ y, const float *__restrict__ eps_f, float w_ll, float w_kl, Workspace ws,
     float *__restrict__ part_out, int slot) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using G = GpF<M, DIN, DX>;
+  using G = GpF<M, DIN, DX, 0>;
   using W = WarpAcc<M, DIN, DX>;
   extern __shared__ __align__(16) float smem[];
   G g;
@@ -539,7 +705,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fw_reverse_fast_kernel(
         for (int j = 0; j < DH; ++j) yt[DY + j] = Hp[j * np];
       }
       const float e = eps_f[(size_t)t * D.n_local + nr];
-      gp_forward_fast<M, DIN, DX>(g, xin, xt, k, a, fm, fv);
+      gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
       const bool do_cond = D.condition || (t < D.R - 1);
       float fmb[DX], fvb[DX], ytb[DX];
       fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
@@ -553,7 +719,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fw_reverse_fast_kernel(
       }
       float xinb[DX];
       __syncwarp();   // previous step's accumulate() has finished reading the staging tile
-      gp_reverse_fast<M, DIN, DX, DX>(g, stg, lane, xt, k, a, fmb, fvb, live, xinb, Lacc, sw, sG);
+      gp_reverse_fast<M, DIN, DX, DX, 0>(g, stg, lane, xt, k, a, fmb, fvb, live, xinb, Lacc, sw, sG);
       __syncwarp();
       wacc.accumulate(stg);
 #pragma unroll
@@ -594,7 +760,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) bm_reverse_fast_kernel(
     const float *__restrict__ y, const float *__restrict__ eps_b, const float *__restrict__ z_b, float w_en,
     Workspace ws, float *__restrict__ part_out, int slot) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using G = GpF<M, DIN, DH>;
+  using G = GpF<M, DIN, DH, 1>;
   using W = WarpAcc<M, DIN, DH>;
   extern __shared__ __align__(16) float smem[];
   G g;
@@ -650,7 +816,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) bm_reverse_fast_kernel(
 #pragma unroll
       for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
       const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
-      gp_forward_fast<M, DIN, DH>(g, xin, xt, k, a, fm, fv);
+      gp_forward_fast<M, DIN, DH, 1>(g, xin, xt, k, a, fm, fv);
       const bool write = writer_run(t, D.R) == ch.run;
       float ob[DH], fvb[DH];
       const float *Yp = ws.Yb + ((size_t)t * DH) * np + nr;
@@ -669,7 +835,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) bm_reverse_fast_kernel(
       }
       float xinb[DH];
       __syncwarp();
-      gp_reverse_fast<M, DIN, DH, DH>(g, stg, lane, xt, k, a, ob, fvb, live, xinb, Lacc, sw, sG);
+      gp_reverse_fast<M, DIN, DH, DH, 1>(g, stg, lane, xt, k, a, ob, fvb, live, xinb, Lacc, sw, sG);
       __syncwarp();
       wacc.accumulate(stg);
 #pragma unroll

@@ -8,8 +8,8 @@ template <int DX, int DU, int DY, int M>
 struct LaunchFast {
   static constexpr int DH = DX - DY, DIN = DX + DU;
   static constexpr int VXP = 4 * ((DX + 3) / 4);
-  using Gf = GpF<M, DIN, DX>;
-  using Gb = GpF<M, DIN, DH>;
+  using Gf = GpF<M, DIN, DX, 0>;
+  using Gb = GpF<M, DIN, DH, 1>;
   using Wf = WarpAcc<M, DIN, DX>;
   using Wb = WarpAcc<M, DIN, DH>;
 
@@ -32,6 +32,17 @@ struct LaunchFast {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
 
+  // Refresh the constant-bank image of one GP (slot 0: forward-rollout GP, 1: message GP).
+  static cudaError_t load_const(int slot, GpDev gp, int dout, float *scratch, cudaStream_t st) {
+    if (!kConstOps) return cudaSuccess;
+    pack_const_kernel<<<1, 256, 0, st>>>(gp, M, DIN, dout, scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t bytes = sizeof(float) * (slot == 0 ? Gf::C::TOTAL : Gb::C::TOTAL);
+    return cudaMemcpyToSymbolAsync(c_ops, scratch, bytes, sizeof(float) * (size_t)slot * kConstFloats,
+                                   cudaMemcpyDeviceToDevice, st);
+  }
+
   static cudaError_t bm_forward(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
                                 const float *y, const float *eps_b, const float *z_b, Workspace ws,
                                 float *part_out, cudaStream_t st) {
@@ -39,6 +50,7 @@ struct LaunchFast {
     const size_t smem = smem_bytes(M, 0);
     cudaError_t e = prep(bm_forward_fast_kernel<DX, DU, DY, M>, smem);
     if (e != cudaSuccess) return e;
+    if ((e = load_const(1, gp, DH, ws.cpack + kConstFloats, st)) != cudaSuccess) return e;
     dim3 grid(ceil_div(D.n_local, kFastThreads), ct.count);
     bm_forward_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
     return cudaGetLastError();
@@ -50,6 +62,7 @@ struct LaunchFast {
     const size_t smem = smem_bytes(M, 1);
     cudaError_t e = prep(fw_forward_fast_kernel<DX, DU, DY, M>, smem);
     if (e != cudaSuccess) return e;
+    if ((e = load_const(0, gp, DX, ws.cpack, st)) != cudaSuccess) return e;
     fw_forward_fast_kernel<DX, DU, DY, M><<<ceil_div(D.n_local, kFastThreads), kFastThreads, smem, st>>>(
         D, gp, vx, vy, u, y, eps_f, ws, part_out);
     return cudaGetLastError();
@@ -61,6 +74,7 @@ struct LaunchFast {
     const size_t smem = smem_bytes(M, 2);
     cudaError_t e = prep(fw_reverse_fast_kernel<DX, DU, DY, M>, smem);
     if (e != cudaSuccess) return e;
+    if ((e = load_const(0, gp, DX, ws.cpack, st)) != cudaSuccess) return e;
     AccLayout Lf, Lb;
     layouts(M, &Lf, &Lb);
     fw_reverse_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws,
@@ -74,6 +88,7 @@ struct LaunchFast {
     const size_t smem = smem_bytes(M, 3);
     cudaError_t e = prep(bm_reverse_fast_kernel<DX, DU, DY, M>, smem);
     if (e != cudaSuccess) return e;
+    if ((e = load_const(1, gp, DH, ws.cpack + kConstFloats, st)) != cudaSuccess) return e;
     AccLayout Lf, Lb;
     layouts(M, &Lf, &Lb);
     bm_reverse_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws,
