@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcbfssm_b200.so")
+LIB_PATH = os.environ.get("CBFSSM_B200_LIB") or os.path.join(_HERE, "libcbfssm_b200.so")   # override: kernel experiments
 
 CBF_ERR = {-1: "CBF_ERR_INVALID_SHAPE", -2: "CBF_ERR_UNSUPPORTED_DIMS", -3: "CBF_ERR_UNSUPPORTED_M",
            -4: "CBF_ERR_ALIGNMENT", -5: "CBF_ERR_NULL"}

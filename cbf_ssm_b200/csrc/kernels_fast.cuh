@@ -19,6 +19,9 @@ namespace cbf {
 
 constexpr int kFastThreads = 128;
 constexpr int kFastWarps = kFastThreads / 32;
+#ifndef CBF_REV_MINBLOCKS
+#define CBF_REV_MINBLOCKS 3
+#endif
 constexpr int kSLD = 36;   // staging row stride (floats): 32 lanes + 4, == 4 mod 32
 
 struct TileCfg {
@@ -32,16 +35,30 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 // (and from the first contraction into the second) and then spills them.
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
-// Minimise issue slots per particle-step of the per-warp accumulation: rounds * (TR*TC FMAs + loads).
+// 2^x as one MUFU.EX2 (exp2f() adds range scaling: two FMULs and a predicate per call).
+// The argument is -0.5*log2(e)*d^2 + log2(sigma^2) <= log2(sigma^2); results below the
+// float32 normal range flush to zero, which is what the kernel value is there anyway.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Tile shape of the per-warp accumulation.  Per 4 particles a lane issues 4*TR*TC FMAs and
+// TR+TC LDS.128; a non-uniform LDS.128 costs >= 4 shared-memory wavefronts (measured) and the
+// SM retires one wavefront per cycle against four FMA issues, so loads are weighted 2 FMAs
+// each.  TC must be odd: the 8 lanes of a quarter-warp read right-operand rows TC apart with a
+// row stride of 36 floats, which is bank-conflict-free only if gcd(TC, 8) = 1 (TC = 2 measured
+// at 8 wavefronts per load instead of 4).
 constexpr TileCfg pick_tiles(int M, int Din, int Dout) {
-  TileCfg best{4, 4, 1000};
+  TileCfg best{4, 5, 1000};
   double best_cost = 1e30;
   for (int tr = 2; tr <= 8; ++tr)
-    for (int tc = 2; tc <= 8; ++tc) {
+    for (int tc = 3; tc <= 7; tc += 2) {
       const int rg = cdiv(M, tr), cg = cdiv(M, tc) + 2 * cdiv(Dout, tc) + cdiv(Din + 1, tc);
       const int rounds = cdiv(rg * cg, 32);
       if (rounds * tr * tc > 50) continue;   // accumulator registers per lane
-      const double cost = rounds * (tr * tc + 0.5 * (tr + tc));
+      const double cost = rounds * (tr * tc + 2.0 * (tr + tc));
       if (cost < best_cost) { best_cost = cost; best = TileCfg{tr, tc, rounds}; }
     }
   return best;
@@ -98,11 +115,16 @@ static __global__ void pack_const_kernel(GpDev g, int M, int DIN, int DOUT, floa
 }
 
 // a = P k with P from the constant bank (upper triangle, each off-diagonal value feeds two FMAs).
-template <int SLOT, int M, int DIN, int DOUT, int MP>
+// With ADD_BASE the result starts from base[] (a += P k), which lets the caller fold an
+// axpy into the contraction and end the live range of its operand early.
+template <int SLOT, int M, int DIN, int DOUT, int MP, bool ADD_BASE = false>
 __device__ __forceinline__ void matvec_const(const float (&k)[MP], float (&a)[MP]) {
   using C = CO<SLOT, M, DIN, DOUT>;
 #pragma unroll
-  for (int m = 0; m < MP; ++m) a[m] = (m < M) ? C::P(m < M ? m : 0, m < M ? m : 0) * k[m] : 0.f;
+  for (int m = 0; m < MP; ++m) {
+    const float d = (m < M) ? C::P(m < M ? m : 0, m < M ? m : 0) * k[m] : 0.f;
+    a[m] = ADD_BASE ? a[m] + d : d;
+  }
   // rectangular loops with a compile-time predicate: unrolls fully, the dead half folds away
 #pragma unroll
   for (int m = 0; m < M; ++m) {
@@ -215,7 +237,7 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
         float d2 = 0.f;
 #pragma unroll
         for (int j = 0; j < DIN; ++j) { const float e = xt[j] - C::Zt(m < M ? m : 0, j); d2 = fmaf(e, e, d2); }
-        k[m] = exp2f(fmaf(kNegHalfLog2e, d2, g.lsig));
+        k[m] = fast_exp2(fmaf(kNegHalfLog2e, d2, g.lsig));
 #pragma unroll
         for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(k[m], C::al(m < M ? m : 0, d), fm[d]);
       } else {
@@ -253,7 +275,7 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
       float d2 = 0.f;
 #pragma unroll
       for (int j = 0; j < DIN; ++j) { const float e = xt[j] - z[j]; d2 = fmaf(e, e, d2); }
-      k[m] = exp2f(fmaf(kNegHalfLog2e, d2, g.lsig));
+      k[m] = fast_exp2(fmaf(kNegHalfLog2e, d2, g.lsig));
       float al[DOUTP];
       ld_row<DOUTP>(g.al + m * DOUTP, al);
 #pragma unroll
@@ -390,14 +412,23 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
         b[m] = 0.f;
       }
     }
-    float pb[MP];
-    matvec_const<SLOT, M, DIN, DOUT, MP>(b, pb);
-#pragma unroll
-    for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
+    // stage the operands that are final now, so that b dies at the end of the contraction
     float *sp = stg + lane;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-      float kb = 2.f * pb[m] - 2.f * Gs * a[m];
+      sp[(W::rowK + m) * kSLD] = k[m];
+      sp[(W::rowAb + m) * kSLD] = 2.f * b[m] - Gs * k[m];
+      sp[(W::rowAsq + m) * kSLD] = a[m] * a[m];
+    }
+    float pb[MP];   // P b - G a, so that a dies here
+#pragma unroll
+    for (int m = 0; m < MP; ++m) pb[m] = -Gs * a[m];
+    matvec_const<SLOT, M, DIN, DOUT, MP, true>(b, pb);
+#pragma unroll
+    for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float kb = 2.f * pb[m];
 #pragma unroll
       for (int d = 0; d < DOUT; ++d) kb = fmaf(C::al(m, d), gm[d], kb);
       const float w = kb * k[m];
@@ -409,9 +440,6 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
         if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
         Lacc[j] = fmaf(wd, dl, Lacc[j]);
       }
-      sp[(W::rowK + m) * kSLD] = k[m];
-      sp[(W::rowAb + m) * kSLD] = 2.f * b[m] - Gs * k[m];
-      sp[(W::rowAsq + m) * kSLD] = a[m] * a[m];
       sp[(W::rowW + m) * kSLD] = w;
     }
 #pragma unroll
@@ -645,7 +673,7 @@ __global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
 // [tile accumulators | L_j, sum w, sum G, var_x_bar, var_y_bar].
 // =====================================================================================
 template <int DX, int DU, int DY, int M>
-__global__ void __launch_bounds__(kFastThreads, 3) fw_reverse_fast_kernel(
+__global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fast_kernel(
     Dims D, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ vyg, const float *__restrict__ u,
     const float *__restrict__ y, const float *__restrict__ eps_f, float w_ll, float w_kl, Workspace ws,
     float *__restrict__ part_out, int slot) {
@@ -755,7 +783,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fw_reverse_fast_kernel(
 }
 
 template <int DX, int DU, int DY, int M>
-__global__ void __launch_bounds__(kFastThreads, 3) bm_reverse_fast_kernel(
+__global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) bm_reverse_fast_kernel(
     Dims D, ChainTable chains, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ u,
     const float *__restrict__ y, const float *__restrict__ eps_b, const float *__restrict__ z_b, float w_en,
     Workspace ws, float *__restrict__ part_out, int slot) {

@@ -1,0 +1,7 @@
+for lib in "" cbf_ssm_b200/libcbf_v2.so; do
+  echo "== lib=$lib"
+  CBFSSM_B200_LIB=${lib:+$PWD/$lib} python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print(d['value'], d['ms_per_step']); print(d['roofline']['kernel_ms_avg'])"
+done
