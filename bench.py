@@ -34,7 +34,17 @@ import numpy as np
 
 METRIC = "elbo_fwd_bwd_particle_steps_per_sec"
 UNIT = "particle-steps/s"
-WORK = dict(dx=4, du=2, dy=2, M=20, S=50, T=300, R=50, kap=1.0, lf=(20.0, 0.0))
+WORKLOADS = {
+    # BASELINE.json configs[1]: the headline workload (default)
+    "robomove_m20": dict(dx=4, du=2, dy=2, M=20, S=50, T=300, R=50, kap=1.0, lf=(20.0, 0.0), batch=4096,
+                         name="RoboMove-shaped CBF-SSM dx4/du2/dy2 M20 S50 T300 R50 (BASELINE.json configs[1])"),
+    # run/template.py defaults (north_star target shape M=100, D=4); secondary, not the driver's line
+    "template_m100": dict(dx=4, du=2, dy=2, M=100, S=50, T=100, R=50, kap=1.0, lf=(10.0, 0.0), batch=1024,
+                          name="run/template.py CBF-SSM dx4/du2/dy2 M100 S50 T100 R50"),
+    "sarcos_m100": dict(dx=14, du=7, dy=7, M=100, S=20, T=250, R=16, kap=50.0, lf=(6.0, 0.0), batch=512,
+                        name="Sarcos-shaped CBF-SSM dx14/du7/dy7 M100 S20 T250 R16 (BASELINE.json configs[2])"),
+}
+WORK = dict(WORKLOADS["robomove_m20"])
 CFG_INIT = dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0)
 
 
@@ -145,7 +155,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "RoboMove-shaped CBF-SSM dx4/du2/dy2 M20 S50 T300 R50 (BASELINE.json configs[1])",
+            "config": {"workload": w["name"],
                        "batch_per_step": 32, **{k: w[k] for k in ("M", "S", "T", "R")}},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "CPU restatement of the TF-1.8 path (oracle/), not TensorFlow: TF 1.8 cannot be installed here"},
@@ -307,7 +317,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "RoboMove-shaped CBF-SSM dx4/du2/dy2 M20 S50 T300 R50 (BASELINE.json configs[1])",
+            "config": {"workload": w["name"],
                        "batch_per_gpu": B, "global_batch": B * world, "particles_per_gpu": N, "seq_len": T,
                        "M": M, "S": S, "R": w["R"], "parallelism": f"dp{world} over sequences, 1 all-reduce/step",
                        "l2": f"inputs larger than L2: {resident_bytes / 2**20:.0f} MiB of draws+data and "
@@ -329,9 +339,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="sequences per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (0 = workload default)")
+    ap.add_argument("--workload", default="robomove_m20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    WORK.clear()
+    WORK.update(WORKLOADS[args.workload])
+    if args.batch <= 0:
+        args.batch = WORK["batch"]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -445,7 +445,7 @@ CBF_API int cbf_supported(int32_t M, int32_t dx, int32_t du, int32_t dy) {
   if (!ops || M < 1) return 0;
   for (int w = 0; w < 4; ++w)
     if (ops->smem_bytes(M, w) > kMaxSmem) return 0;
-  return 1;
+  return ops->fixed_M ? 2 : 1;
 }
 
 CBF_API int cbf_workspace_bytes(const cbf_shape *shape, size_t *bytes_out) {

@@ -44,26 +44,43 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Tile shape of the per-warp accumulation.  Per 4 particles a lane issues 4*TR*TC FMAs and
-// TR+TC LDS.128; a non-uniform LDS.128 costs >= 4 shared-memory wavefronts (measured) and the
-// SM retires one wavefront per cycle against four FMA issues, so loads are weighted 2 FMAs
-// each.  TC must be odd: the 8 lanes of a quarter-warp read right-operand rows TC apart with a
-// row stride of 36 floats, which is bank-conflict-free only if gcd(TC, 8) = 1 (TC = 2 measured
-// at 8 wavefronts per load instead of 4).
+// Tile shape of the per-warp accumulation (packed FP32: two columns per FFMA2).  Per 4
+// particles a lane issues 2*TR*TC FFMA2 and TR+TC LDS.128; a non-uniform LDS.128 costs >= 4
+// shared-memory wavefronts (measured) while the SM retires one wavefront per cycle against four
+// issue slots, so a load is weighted 4.  TC must be 2 or 6: the 8 lanes of a quarter-warp read
+// right-operand pair-rows TC/2 apart with a pair-row stride of 68 floats (17 16-byte granules),
+// which is bank-conflict-free only if TC/2 is odd (TC = 2 with the old unpacked layout measured
+// 8 wavefronts per load instead of 4).
 constexpr TileCfg pick_tiles(int M, int Din, int Dout) {
-  TileCfg best{4, 5, 1000};
+  TileCfg best{5, 6, 1000};
   double best_cost = 1e30;
   for (int tr = 2; tr <= 8; ++tr)
-    for (int tc = 3; tc <= 7; tc += 2) {
+    for (int tc = 2; tc <= 6; tc += 4) {
       const int rg = cdiv(M, tr), cg = cdiv(M, tc) + 2 * cdiv(Dout, tc) + cdiv(Din + 1, tc);
       const int rounds = cdiv(rg * cg, 32);
-      if (rounds * tr * tc > 50) continue;   // accumulator registers per lane
-      const double cost = rounds * (tr * tc + 2.0 * (tr + tc));
+      if (rounds * tr * tc > 60) continue;   // accumulator registers per lane
+      const double cost = rounds * (2.0 * tr * tc + 4.0 * (tr + tc));
       if (cost < best_cost) { best_cost = cost; best = TileCfg{tr, tc, rounds}; }
     }
   return best;
 }
 
+// Packed FP32 FMA (sm_100 FFMA2): d.xy = a.xy * s + c.xy with the scalar s broadcast (ptxas folds
+// the {s,s} pack into the .F32 operand form).  Same FLOP rate as FFMA, half the issue slots
+// (tools/microbench/ffma2.cu: 71 vs 74 TFLOP/s on B200).
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &x, float &y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2_bcast(float ax, float ay, float s, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack2(ax, ay)), "l"(pack2(s, s)), "l"(c));
+  return d;
+}
 
 // ---- resident operands in the constant bank -------------------------------------------
 // Measured on B200 (profiles/r01b_fast_bm_reverse_full.txt + source page): a warp-uniform
@@ -302,24 +319,41 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
 }
 
 // ---- per-warp staging tile + accumulation of the parameter adjoints ----
-// Row map of the warp-private staging tile (each row = 32 lanes, stride kSLD):
-//   right matrix: [k : colGm rows (zero padded)] [g_mean : CGd*TC] [g_var : CGd*TC] [x~,1 : CGx*TC]
-//   left-only   : [a_bar : RG*TR] [a^2 : RG*TR] [w : RG*TR]     (k doubles as a left operand)
+// Warp-private staging tile, rewritten every step by the 32 lanes (lane = particle n):
+//   right matrix, column space of the accumulators  [k | g_mean | g_var | x~,1] (blocks padded to
+//     TC): stored pair-interleaved, element (col, n) at (col/2)*kPS + 2n + (col&1), so one
+//     LDS.128 yields two particles x two adjacent columns = two FFMA2 operand pairs;
+//   left arrays [a_bar | k | a^2 | w], K-major: element (m, n) at (which*LROWS + m)*kSLD + n.
+constexpr int kPS = 68;   // pair-row stride (floats): 64 + 4
 template <int M, int DIN, int DOUT>
 struct WarpAcc {
   static constexpr TileCfg TCFG = pick_tiles(M, DIN, DOUT);
-  static constexpr int TR = TCFG.TR, TC = TCFG.TC, ROUNDS = TCFG.rounds;
+  static constexpr int TR = TCFG.TR, TC = TCFG.TC, ROUNDS = TCFG.rounds, TC2 = TC / 2;
+  static_assert(TC % 2 == 0, "packed accumulation needs an even tile width");
   static constexpr int RG = cdiv(M, TR), CGk = cdiv(M, TC), CGd = cdiv(DOUT, TC), CGx = cdiv(DIN + 1, TC);
-  static constexpr int CG = CGk + 2 * CGd + CGx, NTILES = RG * CG;
-  static constexpr int KROWS = (CGk * TC > RG * TR) ? CGk * TC : RG * TR;
-  static constexpr int rowK = 0, rowGm = KROWS, rowGv = rowGm + CGd * TC, rowX = rowGv + CGd * TC;
-  static constexpr int rowAb = rowX + CGx * TC, rowAsq = rowAb + RG * TR, rowW = rowAsq + RG * TR;
-  static constexpr int ROWS = rowW + RG * TR;
-  static constexpr int FLOATS = ROWS * kSLD;
+  static constexpr int CG = CGk + 2 * CGd + CGx, NTILES = RG * CG, NCOLS = CG * TC;
+  static constexpr int colK = 0, colGm = CGk * TC, colGv = colGm + CGd * TC, colX = colGv + CGd * TC;
+  static constexpr int LROWS = RG * TR;
+  static constexpr int LEFT_OFF = (NCOLS / 2) * kPS;
+  static constexpr int FLOATS = LEFT_OFF + 4 * LROWS * kSLD;
   static constexpr int NACC = NTILES * TR * TC;
+  enum { L_AB = 0, L_K = 1, L_ASQ = 2, L_W = 3 };
 
-  float acc[ROUNDS][TR][TC];
-  int loff[ROUNDS], roff[ROUNDS];   // staging row offsets (floats) of this lane's tiles
+  unsigned long long acc[ROUNDS][TR][TC2];
+  int loff[ROUNDS], roff[ROUNDS];   // staging offsets (floats) of this lane's tiles
+
+  static __device__ __forceinline__ void put_left(float *stg, int lane, int which, int m, float v) {
+    stg[LEFT_OFF + (which * LROWS + m) * kSLD + lane] = v;
+  }
+  // columns col0 .. col0+N-1 of the right matrix (col0 even), two per 64-bit store
+  template <int N, int NMAX>
+  static __device__ __forceinline__ void put_right(float *stg, int lane, int col0, const float (&v)[NMAX]) {
+#pragma unroll
+    for (int c = 0; c < N; c += 2) {
+      const float2 pr = make_float2(v[c], (c + 1 < N) ? v[c + 1 < N ? c + 1 : 0] : 0.f);
+      *reinterpret_cast<float2 *>(stg + ((col0 + c) / 2) * kPS + 2 * lane) = pr;
+    }
+  }
 
   __device__ __forceinline__ void init(int lane) {
 #pragma unroll
@@ -327,17 +361,17 @@ struct WarpAcc {
 #pragma unroll
       for (int i = 0; i < TR; ++i)
 #pragma unroll
-        for (int j = 0; j < TC; ++j) acc[r][i][j] = 0.f;
+        for (int j = 0; j < TC2; ++j) acc[r][i][j] = 0ull;
       int tile = lane + 32 * r;
       if (tile >= NTILES) tile = 0;   // idle slot: recompute tile 0, never written out
       const int rg = tile / CG, cg = tile - rg * CG;
-      int lrow, rrow;
-      if (cg < CGk) { lrow = rowAb; rrow = rowK + cg * TC; }
-      else if (cg < CGk + CGd) { lrow = rowK; rrow = rowGm + (cg - CGk) * TC; }
-      else if (cg < CGk + 2 * CGd) { lrow = rowAsq; rrow = rowGv + (cg - CGk - CGd) * TC; }
-      else { lrow = rowW; rrow = rowX + (cg - CGk - 2 * CGd) * TC; }
-      loff[r] = (lrow + rg * TR) * kSLD;
-      roff[r] = rrow * kSLD;
+      int which;
+      if (cg < CGk) which = L_AB;
+      else if (cg < CGk + CGd) which = L_K;
+      else if (cg < CGk + 2 * CGd) which = L_ASQ;
+      else which = L_W;
+      loff[r] = LEFT_OFF + (which * LROWS + rg * TR) * kSLD;
+      roff[r] = (cg * TC / 2) * kPS;
     }
   }
 
@@ -348,20 +382,23 @@ struct WarpAcc {
       const float *lp = stg + loff[r], *rp = stg + roff[r];
 #pragma unroll 2
       for (int n4 = 0; n4 < 32; n4 += 4) {
-        float4 l[TR], rr[TC];
+        float4 l[TR], r0[TC2], r1[TC2];
 #pragma unroll
         for (int i = 0; i < TR; ++i) l[i] = *reinterpret_cast<const float4 *>(lp + i * kSLD + n4);
 #pragma unroll
-        for (int j = 0; j < TC; ++j) rr[j] = *reinterpret_cast<const float4 *>(rp + j * kSLD + n4);
+        for (int j = 0; j < TC2; ++j) {
+          r0[j] = *reinterpret_cast<const float4 *>(rp + j * kPS + 2 * n4);
+          r1[j] = *reinterpret_cast<const float4 *>(rp + j * kPS + 2 * n4 + 4);
+        }
 #pragma unroll
         for (int i = 0; i < TR; ++i)
 #pragma unroll
-          for (int j = 0; j < TC; ++j) {
-            float c = acc[r][i][j];
-            c = fmaf(l[i].x, rr[j].x, c);
-            c = fmaf(l[i].y, rr[j].y, c);
-            c = fmaf(l[i].z, rr[j].z, c);
-            c = fmaf(l[i].w, rr[j].w, c);
+          for (int j = 0; j < TC2; ++j) {
+            unsigned long long c = acc[r][i][j];
+            c = ffma2_bcast(r0[j].x, r0[j].y, l[i].x, c);
+            c = ffma2_bcast(r0[j].z, r0[j].w, l[i].y, c);
+            c = ffma2_bcast(r1[j].x, r1[j].y, l[i].z, c);
+            c = ffma2_bcast(r1[j].z, r1[j].w, l[i].w, c);
             acc[r][i][j] = c;
           }
       }
@@ -376,7 +413,12 @@ struct WarpAcc {
 #pragma unroll
         for (int i = 0; i < TR; ++i)
 #pragma unroll
-          for (int j = 0; j < TC; ++j) out[((size_t)tile * TR + i) * TC + j] = acc[r][i][j];
+          for (int j = 0; j < TC2; ++j) {
+            float x, y;
+            unpack2(acc[r][i][j], x, y);
+            out[((size_t)tile * TR + i) * TC + 2 * j] = x;
+            out[((size_t)tile * TR + i) * TC + 2 * j + 1] = y;
+          }
       }
     }
   }
@@ -413,13 +455,13 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
       }
     }
     // stage the operands that are final now, so that b dies at the end of the contraction
-    float *sp = stg + lane;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-      sp[(W::rowK + m) * kSLD] = k[m];
-      sp[(W::rowAb + m) * kSLD] = 2.f * b[m] - Gs * k[m];
-      sp[(W::rowAsq + m) * kSLD] = a[m] * a[m];
+      W::put_left(stg, lane, W::L_K, m, k[m]);
+      W::put_left(stg, lane, W::L_AB, m, 2.f * b[m] - Gs * k[m]);
+      W::put_left(stg, lane, W::L_ASQ, m, a[m] * a[m]);
     }
+    W::template put_right<M, MP>(stg, lane, W::colK, k);
     float pb[MP];   // P b - G a, so that a dies here
 #pragma unroll
     for (int m = 0; m < MP; ++m) pb[m] = -Gs * a[m];
@@ -440,16 +482,17 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
         if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
         Lacc[j] = fmaf(wd, dl, Lacc[j]);
       }
-      sp[(W::rowW + m) * kSLD] = w;
+      W::put_left(stg, lane, W::L_W, m, w);
     }
+    W::template put_right<DOUT, DOUT>(stg, lane, W::colGm, gm);
+    W::template put_right<DOUT, DOUT>(stg, lane, W::colGv, gv);
+    {
+      float xr[DIN + 1];
 #pragma unroll
-    for (int d = 0; d < DOUT; ++d) {
-      sp[(W::rowGm + d) * kSLD] = gm[d];
-      sp[(W::rowGv + d) * kSLD] = gv[d];
+      for (int j = 0; j < DIN; ++j) xr[j] = live ? xt[j] : 0.f;
+      xr[DIN] = live ? 1.f : 0.f;
+      W::template put_right<DIN + 1, DIN + 1>(stg, lane, W::colX, xr);
     }
-#pragma unroll
-    for (int j = 0; j < DIN; ++j) sp[(W::rowX + j) * kSLD] = live ? xt[j] : 0.f;
-    sp[(W::rowX + DIN) * kSLD] = live ? 1.f : 0.f;
 #pragma unroll
     for (int j = 0; j < NEED; ++j) xinb[j] *= C::il(j);
     return;
@@ -478,7 +521,6 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
   compiler_fence();
 #pragma unroll
   for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
-  float *sp = stg + lane;
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     float al[DOUTP];
@@ -497,19 +539,21 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
       if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
       Lacc[j] = fmaf(wd, dl, Lacc[j]);
     }
-    sp[(W::rowK + m) * kSLD] = k[m];
-    sp[(W::rowAb + m) * kSLD] = 2.f * b[m] - Gs * k[m];
-    sp[(W::rowAsq + m) * kSLD] = a[m] * a[m];
-    sp[(W::rowW + m) * kSLD] = w;
+    W::put_left(stg, lane, W::L_K, m, k[m]);
+    W::put_left(stg, lane, W::L_AB, m, 2.f * b[m] - Gs * k[m]);
+    W::put_left(stg, lane, W::L_ASQ, m, a[m] * a[m]);
+    W::put_left(stg, lane, W::L_W, m, w);
   }
+  W::template put_right<M, MP>(stg, lane, W::colK, k);
+  W::template put_right<DOUT, DOUT>(stg, lane, W::colGm, gm);
+  W::template put_right<DOUT, DOUT>(stg, lane, W::colGv, gv);
+  {
+    float xr[DIN + 1];
 #pragma unroll
-  for (int d = 0; d < DOUT; ++d) {
-    sp[(W::rowGm + d) * kSLD] = gm[d];
-    sp[(W::rowGv + d) * kSLD] = gv[d];
+    for (int j = 0; j < DIN; ++j) xr[j] = live ? xt[j] : 0.f;
+    xr[DIN] = live ? 1.f : 0.f;
+    W::template put_right<DIN + 1, DIN + 1>(stg, lane, W::colX, xr);
   }
-#pragma unroll
-  for (int j = 0; j < DIN; ++j) sp[(W::rowX + j) * kSLD] = live ? xt[j] : 0.f;
-  sp[(W::rowX + DIN) * kSLD] = live ? 1.f : 0.f;
   {
     float il[DINP];
     ld_row<DINP>(g.il, il);

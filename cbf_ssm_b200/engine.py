@@ -127,7 +127,8 @@ class ElboEngine:
         self.device = torch.device(device)
         self.group = group
         d = dims
-        if not self.lib.cbf_supported(d.ind_pnt_num, d.dim_x, d.dim_u, d.dim_y):
+        self.kernel_path = self.lib.cbf_supported(d.ind_pnt_num, d.dim_x, d.dim_u, d.dim_y)
+        if not self.kernel_path:
             raise _lib.CbfError(-2, f"M={d.ind_pnt_num}, dims=({d.dim_x},{d.dim_u},{d.dim_y}) not supported by the "
                                     "compiled library (csrc/dims_list.h; M limited by shared memory)")
         # ---- flat float64 parameter vector with named views ----
@@ -224,7 +225,9 @@ class ElboEngine:
         self._shape = shape
         self._saved = (u, y, eps_b, z_b, eps_f)
         self._nb = count_chain_batches(T, self.dims.recog_len)
-        self.launches += self._nb + 2
+        # register path: one operand-pack kernel in front of each rollout kernel
+        self._packs = 1 if (self.kernel_path == 2 and not (self.flags & 1)) else 0
+        self.launches += self._nb * (1 + self._packs) + 1 + self._packs + 1
         return self.loss_terms(self.terms)
 
     def loss_terms(self, terms):
@@ -260,7 +263,7 @@ class ElboEngine:
                                                *(gat(f"{tag}.{f}") for f in GP_FIELDS), st))
         check(lib.cbf_noise_backward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
                                      at(gl.var_x), at(gl.var_y), gat("var_x_unc"), gat("var_y_unc"), st))
-        self.launches += 6 + self._nb + 3
+        self.launches += 6 + self._nb * (1 + self._packs) + self._packs + 3
         return self.grad
 
     def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8):

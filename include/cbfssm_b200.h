@@ -85,7 +85,8 @@ typedef struct cbf_grad_layout {
 CBF_API int         cbf_abi_version(void);
 CBF_API const char *cbf_last_error_string(void);
 
-/* 1 if kernels for these dims / this M are compiled in, else 0. */
+/* 0: not supported; 1: cooperative kernels only; 2: register-resident kernels compiled in
+ * for exactly this (M, dims) (used by default). */
 CBF_API int cbf_supported(int32_t M, int32_t dx, int32_t du, int32_t dy);
 
 /* Bytes of caller-allocated device workspace one forward+backward needs. */

@@ -37,7 +37,7 @@ def _shape(**kw):
 
 def test_host_only_entry_points_without_gpu(lib):
     from cbf_ssm_b200._lib import cbf_grad_layout
-    assert lib.cbf_supported(20, 4, 2, 2) == 1
+    assert lib.cbf_supported(20, 4, 2, 2) == 2          # register-resident instantiation
     assert lib.cbf_supported(100, 4, 1, 1) == 1
     assert lib.cbf_supported(100, 14, 7, 7) == 1
     assert lib.cbf_supported(20, 5, 5, 5) == 0          # dims not compiled in
