@@ -481,19 +481,25 @@ CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace ws = bind_workspace(p, workspace);
   const int nch = (int)p.chains.size();
+  // tensor-core forward kernels: a 128-particle tile makes the M x M contraction a real GEMM
+  const bool tc = p.ops->fw_forward_tc != nullptr && shape->M >= 48 && shape->M <= 128 &&
+                  !(shape->flags & (CBF_FLAG_FORCE_COOPERATIVE | CBF_FLAG_NO_TENSOR_CORES)) &&
+                  p.ops->smem_tc(shape->M, 0) <= kMaxSmem && p.ops->smem_tc(shape->M, 1) <= kMaxSmem;
+  const int pt = tc ? ceil_div(p.D.n_local, 128) : p.ptiles;
   for (int c0 = 0; c0 < nch; c0 += kMaxChains) {
     ChainTable ct;
     ct.count = nch - c0 < kMaxChains ? nch - c0 : kMaxChains;
     memcpy(ct.c, p.chains.data() + c0, sizeof(Chain) * ct.count);
     ScopedTiming tm(0, st);
-    CBF_CUDA(p.ops->bm_forward(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, ws,
-                               ws.fpart_bm + (size_t)c0 * p.ptiles, st));
+    CBF_CUDA((tc ? p.ops->bm_forward_tc : p.ops->bm_forward)(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, ws,
+                                                             ws.fpart_bm + (size_t)c0 * pt, st));
   }
   {
     ScopedTiming tm(1, st);
-    CBF_CUDA(p.ops->fw_forward(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, ws, ws.fpart_fw, st));
+    CBF_CUDA((tc ? p.ops->fw_forward_tc : p.ops->fw_forward)(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, ws,
+                                                             ws.fpart_fw, st));
   }
-  finalize_terms_kernel<<<1, 256, 0, st>>>(ws.fpart_bm, nch * p.ptiles, ws.fpart_fw, p.ptiles, p.dy, var_y,
+  finalize_terms_kernel<<<1, 256, 0, st>>>(ws.fpart_bm, nch * pt, ws.fpart_fw, pt, p.dy, var_y,
                                            (double)p.D.n_local * p.D.T, ws.stats, terms);
   CBF_CUDA(cudaGetLastError());
   return 0;

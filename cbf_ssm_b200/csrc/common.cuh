@@ -104,6 +104,13 @@ struct DimOps {
   cudaError_t (*bm_reverse)(const Dims &, const ChainTable &, GpDev, const float *vx, const float *u,
                             const float *y, const float *eps_b, const float *z_b, float w_en, Workspace,
                             float *part_out, int grid, cudaStream_t);
+  // optional tensor-core (tcgen05) forward kernels for large M; nullptr when not compiled in
+  cudaError_t (*bm_forward_tc)(const Dims &, const ChainTable &, GpDev, const float *vx, const float *u,
+                               const float *y, const float *eps_b, const float *z_b, Workspace, float *part_out,
+                               cudaStream_t);
+  cudaError_t (*fw_forward_tc)(const Dims &, GpDev, const float *vx, const float *vy, const float *u,
+                               const float *y, const float *eps_f, Workspace, float *part_out, cudaStream_t);
+  size_t (*smem_tc)(int M, int which);     // which: 0 bm_fwd 1 fw_fwd
   size_t (*smem_bytes)(int M, int which);  // which: 0 bm_fwd 1 fw_fwd 2 fw_rev 3 bm_rev
   int (*occupancy)(int M, int which);      // resident CTAs/SM of the persistent reverse kernels
   void (*layouts)(int M, AccLayout *Lf, AccLayout *Lb);   // accumulator layouts of the two reverse kernels

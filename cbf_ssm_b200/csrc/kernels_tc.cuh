@@ -1,0 +1,452 @@
+// Tensor-core (tcgen05 / TMEM) forward rollout kernels for large M (48 <= M <= 128).
+//
+// For a CTA tile of 128 particles the M x M contraction a = P k of every time step is a real
+// GEMM, D[128 x MP] = K[128 x MP] . P[MP x MP], and runs on the 5th-generation tensor cores:
+//   * one thread = one particle = one TMEM lane; each step the thread evaluates its kernel vector
+//     k' = k / sigma^2 in (0,1] (SIMT: one FFMA chain + one MUFU.EX2 per inducing point), splits it
+//     into two fp16 terms k' = h1 + h2 (22 significant bits together) and stores both as rows of
+//     the K-major A operands K1, K2 in shared memory (canonical no-swizzle core-matrix layout,
+//     16-byte chunk c of row r at c*2048 + r*16: conflict-free 128-bit stores);
+//   * P' = P / 2^e (|P'| <= 1024) is split the same way once per launch into the B operands P1, P2;
+//   * one elected thread issues 3 x MP/16 tcgen05.mma.kind::f16 (K1 P1 + K2 P1 + K1 P2, fp32
+//     accumulation in TMEM; the dropped h2*h2 term is < 2^-22 relative) and commits to an mbarrier;
+//   * every thread reads its accumulator row back with tcgen05.ld (16 columns at a time) and
+//     forms k.a and sum_m a_m^2 S_md in fp32 (SIMT), re-reading its own k' row from K1/K2.
+// The O(M.D) work stays on the SIMT pipes; only the 2 M^2 FLOPs per evaluation move to the tensor
+// pipe.  Reverse-mode kernels for large M still use the cooperative path.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "kernels_fast.cuh"
+
+namespace cbf {
+
+constexpr int kTcThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
+// bits [0,14) start>>4, [16,30) leading-dim byte offset>>4 (between the two 16-byte K chunks of one
+// instruction), [32,46) stride-dim byte offset>>4 (between 8-row groups), [46,48) version = 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): D = fp32, A = B = fp16, both K-major.
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tMBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MBAR_DONE;\n\tbra MBAR_WAIT;\n\tMBAR_DONE:\n\t}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void async_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// x = h1 + h2 with two fp16 terms (round-to-nearest each)
+__device__ __forceinline__ void split_h(float x, __half &h1, __half &h2) {
+  h1 = __float2half_rn(x);
+  h2 = __float2half_rn(x - __half2float(h1));
+}
+
+// Shared-memory state of one CTA: operands, resident small GP tables, barrier, TMEM base.
+template <int DIN, int DOUT>
+struct TcCtx {
+  static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
+  __half *P1, *P2, *K1, *K2;
+  const float *Zt, *al, *Sm, *il;
+  uint32_t bar, tmem, idesc;
+  uint32_t phase;
+  int M, MP;
+  float sig2, pscale;   // P = pscale * P'
+
+  static size_t bytes(int M) {
+    const int MP = round_up(M, 16);
+    return (size_t)2 * MP * MP * 2 + (size_t)2 * kTcThreads * MP * 2 + sizeof(float) * ((size_t)M * (DINP + 2 * DOUTP) + DINP + 4) +
+           64;
+  }
+
+  // Carve + fill (all threads).  Allocates TMEM (warp 0) and initialises the mbarrier.
+  __device__ unsigned char *init(unsigned char *base, const GpDev &g, int M_, float *scratch) {
+    M = M_; MP = round_up(M, 16);
+    P1 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
+    P2 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
+    K1 = reinterpret_cast<__half *>(base); base += (size_t)kTcThreads * MP * 2;
+    K2 = reinterpret_cast<__half *>(base); base += (size_t)kTcThreads * MP * 2;
+    float *Zw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DINP;
+    float *aw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
+    float *Sw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
+    float *iw = reinterpret_cast<float *>(base); base += sizeof(float) * (DINP + 4);
+    uint64_t *barp = reinterpret_cast<uint64_t *>(base); base += 16;
+    uint32_t *tmemp = reinterpret_cast<uint32_t *>(base); base += 16;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // scale of P: |P / 2^e| <= 1024
+    float mx = 0.f;
+    for (int i = tid; i < M * M; i += nt) mx = fmaxf(mx, fabsf(g.P[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) scratch[tid >> 5] = mx;
+    __syncthreads();
+    mx = 0.f;
+    for (int w = 0; w < (nt >> 5); ++w) mx = fmaxf(mx, scratch[w]);
+    int e = 0;
+    frexpf(fmaxf(mx, 1e-30f), &e);   // mx = f * 2^e, f in [0.5, 1)
+    e -= 10;
+    pscale = ldexpf(1.f, e);
+    const float inv = ldexpf(1.f, -e);
+    // B operand: element (n, kk) = P'[kk][n]; K-major chunks: c = kk/8 at c*(MP*8) + n*8 + kk%8
+    for (int i = tid; i < MP * MP; i += nt) {
+      const int c = i / (MP * 8), rem = i - c * (MP * 8), n = rem >> 3, kk = c * 8 + (rem & 7);
+      const float v = (n < M && kk < M) ? g.P[kk * M + n] * inv : 0.f;
+      __half h1, h2;
+      split_h(v, h1, h2);
+      P1[i] = h1;
+      P2[i] = h2;
+    }
+    for (int i = tid; i < M * DINP; i += nt) {
+      const int r = i / DINP, c = i % DINP;
+      Zw[i] = (c < DIN) ? g.Z[r * DIN + c] / g.ell[c] : 0.f;
+    }
+    for (int i = tid; i < M * DOUTP; i += nt) {
+      const int r = i / DOUTP, c = i % DOUTP;
+      aw[i] = (c < DOUT) ? g.alpha[r * DOUT + c] : 0.f;
+      Sw[i] = (c < DOUT) ? g.S[r * DOUT + c] : 0.f;
+    }
+    for (int i = tid; i < DINP; i += nt) iw[i] = (i < DIN) ? 1.f / g.ell[i] : 0.f;
+    Zt = Zw; al = aw; Sm = Sw; il = iw;
+    sig2 = g.sig2[0];
+    bar = smem_u32(barp);
+    idesc = umma_idesc_f16(128, MP);
+    phase = 0;
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (tid < 32) {   // one warp allocates 128 TMEM columns (fp32 accumulator 128 lanes x MP <= 128)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemp)), "r"(128u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    async_proxy_fence();     // P1/P2 written through the generic proxy, read by the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem = *tmemp;
+    return base;
+  }
+
+  __device__ void release() {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+  }
+};
+
+// One sparse-GP evaluation (gp_tf.py:132-161) for the CTA's 128 particles; every thread must call.
+template <int DIN, int DOUT>
+__device__ __forceinline__ void gp_forward_tc(TcCtx<DIN, DOUT> &c, const float (&xin)[DIN], float (&fm)[DOUT],
+                                              float (&fv)[DOUT]) {
+  constexpr int DINP = TcCtx<DIN, DOUT>::DINP, DOUTP = TcCtx<DIN, DOUT>::DOUTP;
+  const int t = threadIdx.x, M = c.M, MP = c.MP;
+  float xt[DINP];
+  {
+    float il[DINP];
+    ld_row<DINP>(c.il, il);
+#pragma unroll
+    for (int j = 0; j < DINP; ++j) xt[j] = (j < DIN) ? xin[j < DIN ? j : 0] * il[j] : 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) fm[d] = 0.f;
+  // ---- kernel vector -> fp16 split operands ----
+  for (int ch = 0; ch < MP / 8; ++ch) {
+    __half h1[8], h2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int m = ch * 8 + e;
+      float kp = 0.f;
+      if (m < M) {
+        float z[DINP];
+        ld_row<DINP>(c.Zt + m * DINP, z);
+        float d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < DIN; ++j) { const float dl = xt[j] - z[j]; d2 = fmaf(dl, dl, d2); }
+        kp = fast_exp2(kNegHalfLog2e * d2);
+        float al[DOUTP];
+        ld_row<DOUTP>(c.al + m * DOUTP, al);
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(kp, al[d], fm[d]);
+      }
+      split_h(kp, h1[e], h2[e]);
+    }
+    const uint4 v1 = make_uint4(pack_h2(h1[0], h1[1]), pack_h2(h1[2], h1[3]), pack_h2(h1[4], h1[5]), pack_h2(h1[6], h1[7]));
+    const uint4 v2 = make_uint4(pack_h2(h2[0], h2[1]), pack_h2(h2[2], h2[3]), pack_h2(h2[4], h2[5]), pack_h2(h2[6], h2[7]));
+    *reinterpret_cast<uint4 *>(c.K1 + (size_t)ch * (kTcThreads * 8) + t * 8) = v1;
+    *reinterpret_cast<uint4 *>(c.K2 + (size_t)ch * (kTcThreads * 8) + t * 8) = v2;
+  }
+  // ---- D = K1 P1 + K2 P1 + K1 P2 on the tensor core ----
+  async_proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    tc_fence_after();
+    const uint32_t lboA = kTcThreads * 16, lboB = MP * 16;
+    const uint32_t a1 = smem_u32(c.K1), a2 = smem_u32(c.K2), b1 = smem_u32(c.P1), b2 = smem_u32(c.P2);
+    const int ks = MP / 16;
+    uint32_t acc = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t ab = (pass == 1) ? a2 : a1, bb = (pass == 2) ? b2 : b1;
+      for (int k = 0; k < ks; ++k) {
+        umma_f16(c.tmem, umma_desc(ab + k * 2 * lboA, lboA, 128), umma_desc(bb + k * 2 * lboB, lboB, 128), c.idesc, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(c.bar);
+  }
+  mbar_wait(c.bar, c.phase);
+  c.phase ^= 1;
+  tc_fence_after();
+  // ---- accumulator row back: q' = k'.a', v'_d = sum a'^2 S ----
+  float q = 0.f;
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
+  const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
+  for (int cc = 0; cc < MP / 16; ++cc) {
+    float a[16];
+    tmem_ld16(trow + cc * 16, a);
+    float kp[16];
+#pragma unroll
+    for (int hch = 0; hch < 2; ++hch) {
+      const size_t off = (size_t)(cc * 2 + hch) * (kTcThreads * 8) + t * 8;
+      const uint4 v1 = *reinterpret_cast<const uint4 *>(c.K1 + off);
+      const uint4 v2 = *reinterpret_cast<const uint4 *>(c.K2 + off);
+      const uint32_t w1[4] = {v1.x, v1.y, v1.z, v1.w}, w2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w1[e]));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w2[e]));
+        kp[hch * 8 + 2 * e] = f1.x + f2.x;
+        kp[hch * 8 + 2 * e + 1] = f1.y + f2.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int m = cc * 16 + e;
+      if (m < M) {
+        q = fmaf(kp[e], a[e], q);
+        const float a2 = a[e] * a[e];
+        float S[DOUTP];
+        ld_row<DOUTP>(c.Sm + m * DOUTP, S);
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, S[d], fv[d]);
+      }
+    }
+  }
+  const float s4 = c.sig2 * c.sig2, ps = c.pscale;
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) {
+    fm[d] *= c.sig2;
+    fv[d] = c.sig2 - ps * s4 * q + ps * ps * s4 * fv[d];
+  }
+  tc_fence_before();   // order this step's tcgen05.ld before the next step's barrier / MMA
+}
+
+// =====================================================================================
+template <int DX, int DU, int DY>
+__global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+                                                                   const float *__restrict__ vxg,
+                                                                   const float *__restrict__ u,
+                                                                   const float *__restrict__ y,
+                                                                   const float *__restrict__ eps_b,
+                                                                   const float *__restrict__ z_b, Workspace ws,
+                                                                   float *__restrict__ part_out) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float scratch[8];
+  __shared__ float vx[16];
+  TcCtx<DIN, DH> c;
+  c.init(smem_raw, gp, D.M, scratch);
+  if (threadIdx.x < DX) vx[threadIdx.x] = vxg[threadIdx.x];
+  __syncthreads();
+
+  const Chain ch = chains.c[blockIdx.y];
+  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const bool live = nl < D.n_local;
+  const int nr = live ? nl : 0;
+  const int b = (D.n_offset + nr) / D.S;
+  const float *ub = u + (size_t)b * D.T * DU;
+  const float *yb = y + (size_t)b * D.T * DY;
+  const size_t np = ws.npad;
+
+  float h[DH], ent = 0.f;
+  {
+    const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + ch.t_hi) * D.n_local + nr] : 0.f;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) h[j] = z;
+  }
+#pragma unroll 1
+  for (int t = ch.t_hi; t >= ch.t_lo; --t) {
+    float xin[DIN], fm[DH], fv[DH];
+#pragma unroll
+    for (int j = 0; j < DH; ++j) xin[j] = h[j];
+#pragma unroll
+    for (int j = 0; j < DU; ++j) xin[DH + j] = ub[t * DU + j];
+#pragma unroll
+    for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
+    const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
+    gp_forward_tc<DIN, DH>(c, xin, fm, fv);
+    const bool write = writer_run(t, D.R) == ch.run;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) {
+      const float f = fv[j] + vx[j];
+      h[j] = fm[j] + h[j] + e * sqrtf(f);
+      if (write) ent += 0.5f * (kLog2PiE + logf(f));
+    }
+    if (live) {
+      float *Hp = ws.H + (((size_t)ch.run * D.T + t) * DH) * np + nl;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) Hp[j * np] = h[j];
+    }
+  }
+  c.release();
+  const float v[1] = {live ? ent : 0.f};
+  cta_sum_store<1>(v, scratch, part_out + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
+}
+
+template <int DX, int DU, int DY>
+__global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+                                                                   const float *__restrict__ vyg,
+                                                                   const float *__restrict__ u,
+                                                                   const float *__restrict__ y,
+                                                                   const float *__restrict__ eps_f, Workspace ws,
+                                                                   float *__restrict__ part_out) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float scratch[4 * (DY + 1)];
+  __shared__ float vx[16], vy[16];
+  TcCtx<DIN, DX> c;
+  c.init(smem_raw, gp, D.M, scratch);
+  if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
+  __syncthreads();
+
+  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const bool live = nl < D.n_local;
+  const int nr = live ? nl : 0;
+  const int b = (D.n_offset + nr) / D.S;
+  const float *ub = u + (size_t)b * D.T * DU;
+  const float *yb = y + (size_t)b * D.T * DY;
+  const size_t np = ws.npad;
+
+  auto load_ytil = [&](int t, float(&yt)[DX]) {
+#pragma unroll
+    for (int j = 0; j < DY; ++j) yt[j] = yb[t * DY + j];
+    const float *Hp = ws.H + (((size_t)writer_run(t, D.R) * D.T + t) * DH) * np + nr;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) yt[DY + j] = Hp[j * np];
+  };
+
+  float x[DX], sse[DY + 1], kl = 0.f;
+#pragma unroll
+  for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
+  load_ytil(0, x);
+#pragma unroll 1
+  for (int t = 0; t < D.T; ++t) {
+    if (live) {
+      float *Xp = ws.X + ((size_t)t * DX) * np + nl;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) Xp[j * np] = x[j];
+#pragma unroll
+      for (int j = 0; j < DY; ++j) { const float d = yb[t * DY + j] - x[j]; sse[j] = fmaf(d, d, sse[j]); }
+    }
+    if (t == D.T - 1) break;
+    float xin[DIN], fm[DX], fv[DX], yt[DX], xn[DX];
+#pragma unroll
+    for (int j = 0; j < DX; ++j) xin[j] = x[j];
+#pragma unroll
+    for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
+    load_ytil(t + 1, yt);
+    const float e = eps_f[(size_t)t * D.n_local + nr];
+    gp_forward_tc<DIN, DX>(c, xin, fm, fv);
+    const bool do_cond = D.condition || (t < D.R - 1);
+    fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, xn, kl);
+#pragma unroll
+    for (int j = 0; j < DX; ++j) x[j] = xn[j];
+  }
+  c.release();
+  sse[DY] = kl;
+  if (!live) {
+#pragma unroll
+    for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
+  }
+  cta_sum_store<DY + 1>(sse, scratch, part_out + (size_t)blockIdx.x * (DY + 1));
+}
+
+template <int DX, int DU, int DY>
+struct LaunchTc {
+  static constexpr int DH = DX - DY, DIN = DX + DU;
+  static size_t smem_b(int M) { return TcCtx<DIN, DH>::bytes(M); }
+  static size_t smem_f(int M) { return TcCtx<DIN, DX>::bytes(M); }
+
+  static cudaError_t bm_forward(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
+                                const float *y, const float *eps_b, const float *z_b, Workspace ws,
+                                float *part_out, cudaStream_t st) {
+    if (ct.count == 0) return cudaSuccess;
+    const size_t smem = smem_b(D.M);
+    cudaError_t e = cudaFuncSetAttribute(bm_forward_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(ceil_div(D.n_local, kTcThreads), ct.count);
+    bm_forward_tc_kernel<DX, DU, DY><<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
+    return cudaGetLastError();
+  }
+  static cudaError_t fw_forward(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
+                                const float *y, const float *eps_f, Workspace ws, float *part_out,
+                                cudaStream_t st) {
+    const size_t smem = smem_f(D.M);
+    cudaError_t e = cudaFuncSetAttribute(fw_forward_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fw_forward_tc_kernel<DX, DU, DY><<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(D, gp, vx, vy, u, y,
+                                                                                             eps_f, ws, part_out);
+    return cudaGetLastError();
+  }
+};
+
+}  // namespace cbf

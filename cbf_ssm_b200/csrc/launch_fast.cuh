@@ -121,6 +121,9 @@ DimOps make_fast_ops() {
   o.fw_forward = &L::fw_forward;
   o.fw_reverse = &L::fw_reverse;
   o.bm_reverse = &L::bm_reverse;
+  o.bm_forward_tc = nullptr;
+  o.fw_forward_tc = nullptr;
+  o.smem_tc = nullptr;
   o.smem_bytes = &L::smem_bytes;
   o.occupancy = &L::occupancy;
   o.layouts = &L::layouts;

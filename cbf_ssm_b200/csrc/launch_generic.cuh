@@ -1,6 +1,7 @@
 // Host launchers for one (dx,du,dy) instantiation of the kernel templates.
 #pragma once
 #include "kernels_generic.cuh"
+#include "kernels_tc.cuh"
 
 namespace cbf {
 
@@ -115,6 +116,9 @@ DimOps make_ops() {
   o.fw_forward = &Launch<DX, DU, DY>::fw_forward;
   o.fw_reverse = &Launch<DX, DU, DY>::fw_reverse;
   o.bm_reverse = &Launch<DX, DU, DY>::bm_reverse;
+  o.bm_forward_tc = &LaunchTc<DX, DU, DY>::bm_forward;
+  o.fw_forward_tc = &LaunchTc<DX, DU, DY>::fw_forward;
+  o.smem_tc = [](int M, int which) { return which == 0 ? LaunchTc<DX, DU, DY>::smem_b(M) : LaunchTc<DX, DU, DY>::smem_f(M); };
   o.smem_bytes = &Launch<DX, DU, DY>::smem_bytes;
   o.occupancy = &Launch<DX, DU, DY>::occupancy;
   o.layouts = &Launch<DX, DU, DY>::layouts;

@@ -61,6 +61,8 @@ typedef struct cbf_shape {
 /* Use the cooperative shared-memory kernels even when a register-resident
  * instantiation for this (dims, M) is compiled in (parity tests cover both). */
 #define CBF_FLAG_FORCE_COOPERATIVE 1
+/* Do not use the tcgen05 tensor-core forward kernels (selected by default for 48 <= M <= 128). */
+#define CBF_FLAG_NO_TENSOR_CORES 2
 
 /* Kernel-level operands of one sparse GP (gp_tf.py:103-130), float32, produced by
  * cbf_gp_prologue (or by the caller).  Dout = dx for gp_f, dx-dy for gp_b. */
