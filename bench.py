@@ -196,6 +196,7 @@ def run_b200(args):
     # each rank owns B whole sequences (weak scaling); gradients/terms are all-reduced
     model = CBFSSM(config, device=dev, group=None, seed=1)
     eng = model.engine
+    eng.flags = args.flags
     eng.group = group
     if world > 1:
         dist.broadcast(eng.theta, src=0)
@@ -342,6 +343,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (0 = workload default)")
     ap.add_argument("--workload", default="robomove_m20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="cbf_shape.flags (1 cooperative kernels, 2 no tensor cores)")
     args = ap.parse_args()
     WORK.clear()
     WORK.update(WORKLOADS[args.workload])

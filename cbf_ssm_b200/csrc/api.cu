@@ -70,6 +70,8 @@ struct ScopedTiming {
 
 constexpr int kMaxGridRev = 148 * 8;   // upper bound on persistent reverse CTAs (workspace sizing)
 constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kMinParticlesRegisterPath = 4096;   // one-thread-per-particle kernels below this are latency-bound
+constexpr int kMinParticlesTensorPath = 12288;    // 128-particle tcgen05 tiles need ~100 CTAs to pay off
 
 // Live chain segments of both backward-message runs (cbfssm.py:123-136, SURVEY 8a note 5).
 static std::vector<Chain> build_chains(int T, int R) {
@@ -115,7 +117,12 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
     return CBF_ERR_INVALID_SHAPE;
   }
   p.dx = s->dx; p.du = s->du; p.dy = s->dy; p.dh = s->dx - s->dy; p.din = s->dx + s->du;
-  p.ops = find_ops(s->dx, s->du, s->dy, s->M, !(s->flags & CBF_FLAG_FORCE_COOPERATIVE));
+  // Kernel selection (measured, tools/bench_small.sh): the register-resident kernels need enough
+  // particles to fill the SMs with one particle per thread; below that the cooperative kernels,
+  // which split one particle's M-loop over several warps, have the shorter serial chain per step.
+  const bool want_fast = !(s->flags & CBF_FLAG_FORCE_COOPERATIVE) &&
+                         ((s->flags & CBF_FLAG_FORCE_REGISTER) || s->n_local >= kMinParticlesRegisterPath);
+  p.ops = find_ops(s->dx, s->du, s->dy, s->M, want_fast);
   if (need_ops && !p.ops) {
     set_error("dims (dx=%d,du=%d,dy=%d) are not compiled in (see csrc/dims_list.h)", s->dx, s->du, s->dy);
     return CBF_ERR_UNSUPPORTED_DIMS;
@@ -484,6 +491,7 @@ CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const c
   // tensor-core forward kernels: a 128-particle tile makes the M x M contraction a real GEMM
   const bool tc = p.ops->fw_forward_tc != nullptr && shape->M >= 48 && shape->M <= 128 &&
                   !(shape->flags & (CBF_FLAG_FORCE_COOPERATIVE | CBF_FLAG_NO_TENSOR_CORES)) &&
+                  ((shape->flags & CBF_FLAG_FORCE_TENSOR_CORES) || shape->n_local >= kMinParticlesTensorPath) &&
                   p.ops->smem_tc(shape->M, 0) <= kMaxSmem && p.ops->smem_tc(shape->M, 1) <= kMaxSmem;
   const int pt = tc ? ceil_div(p.D.n_local, 128) : p.ptiles;
   for (int c0 = 0; c0 < nch; c0 += kMaxChains) {

@@ -63,6 +63,11 @@ typedef struct cbf_shape {
 #define CBF_FLAG_FORCE_COOPERATIVE 1
 /* Do not use the tcgen05 tensor-core forward kernels (selected by default for 48 <= M <= 128). */
 #define CBF_FLAG_NO_TENSOR_CORES 2
+/* By default the register-resident kernels are used from 4096 particles per call and the
+ * tensor-core forward kernels from 12288 (below that the cooperative kernels have the lower
+ * latency per time step).  These flags select them regardless of the particle count. */
+#define CBF_FLAG_FORCE_REGISTER 4
+#define CBF_FLAG_FORCE_TENSOR_CORES 8
 
 /* Kernel-level operands of one sparse GP (gp_tf.py:103-130), float32, produced by
  * cbf_gp_prologue (or by the caller).  Dout = dx for gp_f, dx-dy for gp_b. */

@@ -16,7 +16,7 @@ TOL = 1e-4
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("flags", [0, 1], ids=["default", "cooperative"])
+@pytest.mark.parametrize("flags", [12, 1], ids=["register_or_tensor", "cooperative"])
 @pytest.mark.parametrize("name", list(NAMED_CASES))
 def test_named_configuration_matches_golden(name, flags):
     gold = np.load(os.path.join(GOLD, name + ".npz"))

@@ -53,12 +53,13 @@ CASES = [
     (13, 6, 7, 20, 40, 4, 12, 4, 1.0, (20.0, 0.2), True, False),
 ]
 
-# 0: default kernel selection (register-resident kernels when compiled in);
-# 1: CBF_FLAG_FORCE_COOPERATIVE (shared-memory cooperative kernels)
-PATHS = [0, 1]
+# 12 = CBF_FLAG_FORCE_REGISTER | CBF_FLAG_FORCE_TENSOR_CORES: the register-resident kernels
+#      (small M) / tcgen05 forward kernels (M >= 48) regardless of the particle count;
+# 1  = CBF_FLAG_FORCE_COOPERATIVE: shared-memory cooperative kernels only
+PATHS = [12, 1]
 
 
-@pytest.mark.parametrize("flags", PATHS, ids=["default", "cooperative"])
+@pytest.mark.parametrize("flags", PATHS, ids=["register_or_tensor", "cooperative"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "dx%d_du%d_dy%d_M%d_S%d_B%d_T%d_R%d" % c[:8])
 def test_elbo_and_gradients_match_oracle(case, flags):
     dx, du, dy, M, S, B, T, R, kap, lf, cond, strong = case
@@ -89,7 +90,7 @@ def test_elbo_and_gradients_match_oracle(case, flags):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("flags", PATHS, ids=["default", "cooperative"])
+@pytest.mark.parametrize("flags", PATHS, ids=["register_or_tensor", "cooperative"])
 def test_kernel_level_gradients_match_kernel_math(flags):
     cfg, params, u, y, eps_b, z_b, eps_f = make_problem(4, 2, 2, 7, 3, 2, 11, 3, 1.0, (10.0, 0.5), seed=3, strong=True)
     pn = {k: v.numpy() for k, v in params.items()}

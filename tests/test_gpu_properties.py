@@ -36,7 +36,7 @@ def _inputs(eng, B, T, seed=0):
     return u, y, eb, zb, ef
 
 
-@pytest.mark.parametrize("flags", [0, 1], ids=["default", "cooperative"])
+@pytest.mark.parametrize("flags", [12, 1], ids=["register_or_tensor", "cooperative"])
 def test_sum_of_particle_shards_equals_the_whole_at_bench_shape(flags):
     """Data-parallel contract at the BASELINE shape (M=20, T=300, S=50): the
     kernel-level gradient and the ELBO terms of contiguous particle shards add up to the
@@ -94,12 +94,13 @@ EDGE = [
 ]
 
 
+@pytest.mark.parametrize("flags", [12, 1, 0], ids=["register_or_tensor", "cooperative", "default"])
 @pytest.mark.parametrize("case", EDGE, ids=lambda c: "M%d_S%d_B%d_T%d_R%d_c%d" % (c[3], c[4], c[5], c[6], c[7], c[8]))
-def test_edge_shapes_match_oracle(case):
+def test_edge_shapes_match_oracle(case, flags):
     dx, du, dy, M, S, B, T, R, cond = case
     cfg, params, u, y, eb, zb, ef = make_problem(dx, du, dy, M, S, B, T, R, 1.0, (10.0, 0.5), seed=21, strong=True)
     res, gd = O.loss_and_grads(cfg, params, u, y, eb, zb, ef, cond)
-    eng, out, _ = run_engine(cfg, params, u, y, eb, zb, ef, cond)
+    eng, out, _ = run_engine(cfg, params, u, y, eb, zb, ef, cond, flags)
     assert float(out["loss"]) == pytest.approx(float(res.loss.detach()), rel=1e-4)
     grads = eng.get_grads()
     bad = {k: rel_inf(grads[k], gd[k].numpy()) for k in O.PARAM_NAMES}
