@@ -4,6 +4,8 @@
 #include <string.h>
 #include <vector>
 
+#include <cublas_v2.h>
+
 #include "common.cuh"
 #include "dims_list.h"
 
@@ -90,9 +92,11 @@ static std::vector<Chain> build_chains(int T, int R) {
       for (int t = t_hi; t > t_next; --t)
         if (writer_run(t, R) == run) t_lo = t;
       if (t_lo < 0) continue;   // segment writes nothing: dead work
-      out.push_back(Chain{run, t_hi, t_lo, resample ? 1 : 0});
+      out.push_back(Chain{run, t_hi, t_lo, resample ? 1 : 0, 0});
     }
   }
+  int col = 0;
+  for (Chain &c : out) { c.col0 = col; col += c.t_hi - c.t_lo + 1; }
   return out;
 }
 
@@ -104,7 +108,16 @@ struct Plan {
   AccLayout Lf, Lb;
   size_t off_X, off_H, off_Yb, off_fbm, off_ffw, off_gf, off_gb, off_accf, off_accb, off_stats, off_cpack, total;
   const DimOps *ops;
+  // tensor-core path (48 <= M <= 128, enough particles)
+  bool tc_fwd, tc_rev;
+  size_t colsf, colsb;           // columns (live steps x particles) of the operand matrices
+  int ctot_f, ctot_b, nb_f, nb_b, nsc_f, nsc_b, nspart_f, nspart_b;
+  size_t off_mf, off_mb, off_spf, off_spb, off_rbf, off_rbb, off_rdf, off_rdb, off_blas;
 };
+
+constexpr size_t kTcChunk = 32768;              // columns per SGEMM (float32 inside, float64 across)
+constexpr size_t kBlasWorkspace = 32u << 20;
+constexpr size_t kTcMaxMatBytes = (size_t)96 << 30;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -163,8 +176,58 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   p.off_accb = o; o = align_up(o + sizeof(double) * p.Lb.slot(), 256);
   p.off_stats = o; o = align_up(o + sizeof(double) * (p.dy + 2), 256);
   p.off_cpack = o; o = align_up(o + sizeof(float) * 2 * 2048, 256);
+  // ---- tensor-core path ----
+  p.tc_fwd = p.tc_rev = false;
+  if (p.ops && p.ops->fw_forward_tc != nullptr && s->M >= 48 && s->M <= 128 &&
+      !(s->flags & (CBF_FLAG_FORCE_COOPERATIVE | CBF_FLAG_NO_TENSOR_CORES)) &&
+      ((s->flags & CBF_FLAG_FORCE_TENSOR_CORES) || s->n_local >= kMinParticlesTensorPath)) {
+    p.tc_fwd = p.ops->smem_tc(s->M, 0) <= kMaxSmem && p.ops->smem_tc(s->M, 1) <= kMaxSmem;
+    int live = 0;
+    for (const Chain &c : p.chains) live += c.t_hi - c.t_lo + 1;
+    p.colsf = (size_t)(s->T > 1 ? s->T - 1 : 0) * s->n_local;
+    p.colsb = (size_t)live * s->n_local;
+    p.ctot_f = s->M + 2 * p.dx + p.din + 1;
+    p.ctot_b = s->M + 2 * p.dh + p.din + 1;
+    const size_t rows_f = (size_t)4 * s->M + 2 * p.dx + p.din + 1, rows_b = (size_t)4 * s->M + 2 * p.dh + p.din + 1;
+    const size_t bytes = sizeof(float) * (rows_f * p.colsf + rows_b * p.colsb);
+    p.tc_rev = p.tc_fwd && p.ops->fw_reverse_tc != nullptr && p.ops->smem_tc(s->M, 2) <= kMaxSmem &&
+               p.ops->smem_tc(s->M, 3) <= kMaxSmem && bytes <= kTcMaxMatBytes && p.colsf > 0 && p.colsb > 0 &&
+               p.colsf < ((size_t)1 << 31) && p.colsb < ((size_t)1 << 31);
+    if (p.tc_rev) {
+      p.nb_f = (int)((p.colsf + kTcChunk - 1) / kTcChunk);
+      p.nb_b = (int)((p.colsb + kTcChunk - 1) / kTcChunk);
+      p.nsc_f = p.Lf.slot() - p.Lf.scal_off();
+      p.nsc_b = p.Lb.slot() - p.Lb.scal_off();
+      const int pt = ceil_div(s->n_local, 128);
+      p.nspart_f = pt;
+      p.nspart_b = pt * (int)p.chains.size();
+      p.off_mf = o; o = align_up(o + sizeof(float) * rows_f * p.colsf, 256);
+      p.off_mb = o; o = align_up(o + sizeof(float) * rows_b * p.colsb, 256);
+      p.off_spf = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_f * p.nsc_f, 256);
+      p.off_spb = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_b * p.nsc_b, 256);
+      p.off_rbf = o; o = align_up(o + sizeof(float) * (size_t)p.nb_f * s->M * p.ctot_f, 256);
+      p.off_rbb = o; o = align_up(o + sizeof(float) * (size_t)p.nb_b * s->M * p.ctot_b, 256);
+      p.off_rdf = o; o = align_up(o + sizeof(double) * (size_t)s->M * p.ctot_f, 256);
+      p.off_rdb = o; o = align_up(o + sizeof(double) * (size_t)s->M * p.ctot_b, 256);
+      p.off_blas = o; o = align_up(o + kBlasWorkspace, 256);
+    }
+  }
   p.total = o;
   return 0;
+}
+
+static TcMats bind_mats(void *base, size_t off, size_t L, int M, int dout, int din) {
+  float *f = reinterpret_cast<float *>(static_cast<char *>(base) + off);
+  TcMats m;
+  m.L = L;
+  m.K = f; f += (size_t)M * L;
+  m.Ab = f; f += (size_t)M * L;
+  m.A2 = f; f += (size_t)M * L;
+  m.W = f; f += (size_t)M * L;
+  m.Gm = f; f += (size_t)dout * L;
+  m.Gv = f; f += (size_t)dout * L;
+  m.X1 = f;
+  return m;
 }
 
 static Workspace bind_workspace(const Plan &p, void *base) {
@@ -278,6 +341,32 @@ __global__ void finalize_gp_grad_kernel(AccLayout L, const double *__restrict__ 
   const double *sc = acc + L.scal_off();
   for (int j = tid; j < Din; j += nt) gell[j] = sc[j] / (double)gp.ell[j];
   if (tid == 0) gsig2[0] = sc[Din] / (double)gp.sig2[0] + sc[Din + 1];
+}
+
+// Tensor path: R[m][c] (float64) = sum over (step, particle) of left[m] * right[c] with column blocks
+// [a_bar k'^T (M) | k' g_mean^T (Dout) | a^2 g_var^T (Dout) | w [x~,1]^T (Din+1)]; sc = scalar sums.
+__global__ void finalize_tc_grad_kernel(int M, int Din, int Dout, int Ctot, const double *__restrict__ R,
+                                        const double *__restrict__ sc, GpDev gp, double *__restrict__ gP,
+                                        double *__restrict__ galpha, double *__restrict__ gS,
+                                        double *__restrict__ gZ, double *__restrict__ gell,
+                                        double *__restrict__ gsig2) {
+  const double sig2 = (double)gp.sig2[0];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = tid; i < M * M; i += nt) gP[i] = sig2 * R[(size_t)(i / M) * Ctot + (i % M)];
+  for (int i = tid; i < M * Dout; i += nt) {
+    const int m = i / Dout, d = i % Dout;
+    galpha[i] = sig2 * R[(size_t)m * Ctot + M + d];
+    gS[i] = R[(size_t)m * Ctot + M + Dout + d];
+  }
+  const int xc = M + 2 * Dout;
+  for (int i = tid; i < M * Din; i += nt) {
+    const int m = i / Din, j = i % Din;
+    const double ell = (double)gp.ell[j];
+    const double zt = (double)gp.Z[i] / ell;
+    gZ[i] = (R[(size_t)m * Ctot + xc + j] - zt * R[(size_t)m * Ctot + xc + Din]) / ell;
+  }
+  for (int j = tid; j < Din; j += nt) gell[j] = sc[j] / (double)gp.ell[j];
+  if (tid == 0) gsig2[0] = sc[Din] / sig2 + sc[Din + 1];
 }
 
 __global__ void finalize_noise_grad_kernel(int dx, int dy, int Din, const double *__restrict__ sc_f,
@@ -428,6 +517,47 @@ static int check_gp(const cbf_gp *g, const char *name) {
   return 0;
 }
 
+static thread_local cublasHandle_t g_blas = nullptr;
+
+static const char *blas_status(cublasStatus_t st) {
+  switch (st) {
+    case CUBLAS_STATUS_SUCCESS: return "success";
+    case CUBLAS_STATUS_NOT_INITIALIZED: return "not initialized";
+    case CUBLAS_STATUS_ALLOC_FAILED: return "alloc failed";
+    case CUBLAS_STATUS_INVALID_VALUE: return "invalid value";
+    case CUBLAS_STATUS_EXECUTION_FAILED: return "execution failed";
+    default: return "error";
+  }
+}
+
+// R[nb][M x Ctot] (float32) <- chunked outer-product sums of one GP's operand matrices:
+// block (left, right, C) at column c0: R[:, c0:c0+C] = left[M x L] . right[C x L]^T, one SGEMM per chunk of
+// kTcChunk columns (float32 accumulation inside a chunk only).
+static int tc_gemms(cublasHandle_t h, const TcMats &m, int M, int dout, int din, int Ctot, float *R) {
+  const float one = 1.f, zero = 0.f;
+  const size_t L = m.L, nfull = L / kTcChunk, rem = L - nfull * kTcChunk;
+  const float *left[4] = {m.Ab, m.K, m.A2, m.W};
+  const float *right[4] = {m.K, m.Gm, m.Gv, m.X1};
+  const int C[4] = {M, dout, dout, din + 1};
+  int c0 = 0;
+  for (int b = 0; b < 4; ++b) {
+    cublasStatus_t st = CUBLAS_STATUS_SUCCESS;
+    if (nfull > 0)
+      st = cublasSgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, C[b], M, (int)kTcChunk, &one, right[b], (int)L,
+                                     (long long)kTcChunk, left[b], (int)L, (long long)kTcChunk, &zero, R + c0, Ctot,
+                                     (long long)M * Ctot, (int)nfull);
+    if (st == CUBLAS_STATUS_SUCCESS && rem > 0)
+      st = cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, C[b], M, (int)rem, &one, right[b] + nfull * kTcChunk, (int)L,
+                       left[b] + nfull * kTcChunk, (int)L, &zero, R + nfull * (size_t)M * Ctot + c0, Ctot);
+    if (st != CUBLAS_STATUS_SUCCESS) {
+      set_error("cuBLAS SGEMM failed: %s", blas_status(st));
+      return 700 + (int)st;
+    }
+    c0 += C[b];
+  }
+  return 0;
+}
+
 #define CBF_CUDA(expr)                                                         \
   do {                                                                         \
     cudaError_t _e = (expr);                                                   \
@@ -489,10 +619,7 @@ CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const c
   Workspace ws = bind_workspace(p, workspace);
   const int nch = (int)p.chains.size();
   // tensor-core forward kernels: a 128-particle tile makes the M x M contraction a real GEMM
-  const bool tc = p.ops->fw_forward_tc != nullptr && shape->M >= 48 && shape->M <= 128 &&
-                  !(shape->flags & (CBF_FLAG_FORCE_COOPERATIVE | CBF_FLAG_NO_TENSOR_CORES)) &&
-                  ((shape->flags & CBF_FLAG_FORCE_TENSOR_CORES) || shape->n_local >= kMinParticlesTensorPath) &&
-                  p.ops->smem_tc(shape->M, 0) <= kMaxSmem && p.ops->smem_tc(shape->M, 1) <= kMaxSmem;
+  const bool tc = p.tc_fwd;
   const int pt = tc ? ceil_div(p.D.n_local, 128) : p.ptiles;
   for (int c0 = 0; c0 < nch; c0 += kMaxChains) {
     ChainTable ct;
@@ -532,6 +659,50 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
   const float w_ll = (float)term_weights_host[0], w_kl = (float)term_weights_host[1],
               w_en = (float)term_weights_host[2];
 
+  const int nch = (int)p.chains.size();
+  if (p.tc_rev) {
+    // ---- tensor-core path: rollout adjoints on tcgen05, parameter outer products as chunked SGEMMs ----
+    char *wb = static_cast<char *>(workspace);
+    const TcMats mf = bind_mats(workspace, p.off_mf, p.colsf, p.D.M, p.dx, p.din);
+    const TcMats mb = bind_mats(workspace, p.off_mb, p.colsb, p.D.M, p.dh, p.din);
+    float *spf = reinterpret_cast<float *>(wb + p.off_spf), *spb = reinterpret_cast<float *>(wb + p.off_spb);
+    float *rbf = reinterpret_cast<float *>(wb + p.off_rbf), *rbb = reinterpret_cast<float *>(wb + p.off_rbb);
+    double *rdf = reinterpret_cast<double *>(wb + p.off_rdf), *rdb = reinterpret_cast<double *>(wb + p.off_rdb);
+    {
+      ScopedTiming tm(2, st);
+      CBF_CUDA(p.ops->fw_reverse_tc(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, mf, spf, p.nsc_f, st));
+    }
+    const int pt = ceil_div(p.D.n_local, 128);
+    for (int c0 = 0; c0 < nch; c0 += kMaxChains) {
+      ChainTable ct;
+      ct.count = nch - c0 < kMaxChains ? nch - c0 : kMaxChains;
+      memcpy(ct.c, p.chains.data() + c0, sizeof(Chain) * ct.count);
+      ScopedTiming tm(3, st);
+      CBF_CUDA(p.ops->bm_reverse_tc(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, w_en, ws, mb,
+                                    spb + (size_t)c0 * pt * p.nsc_b, p.nsc_b, st));
+    }
+    reduce_slots_kernel<<<ceil_div(p.nsc_f, 256), 256, 0, st>>>(spf, p.nspart_f, p.nsc_f, ws.acc_f + p.Lf.scal_off());
+    reduce_slots_kernel<<<ceil_div(p.nsc_b, 256), 256, 0, st>>>(spb, p.nspart_b, p.nsc_b, ws.acc_b + p.Lb.scal_off());
+    CBF_CUDA(cudaGetLastError());
+    if (!g_blas) {
+      cublasStatus_t bs = cublasCreate(&g_blas);
+      if (bs != CUBLAS_STATUS_SUCCESS) { g_blas = nullptr; set_error("cublasCreate failed: %s", blas_status(bs)); return 700 + (int)bs; }
+    }
+    cublasSetStream(g_blas, st);
+    cublasSetWorkspace(g_blas, wb + p.off_blas, kBlasWorkspace);
+    cublasSetMathMode(g_blas, CUBLAS_DEFAULT_MATH);       // SGEMM: float32 FMA accumulation (TF32 is opt-in only)
+    if ((rc = tc_gemms(g_blas, mf, p.D.M, p.dx, p.din, p.ctot_f, rbf))) return rc;
+    if ((rc = tc_gemms(g_blas, mb, p.D.M, p.dh, p.din, p.ctot_b, rbb))) return rc;
+    reduce_slots_kernel<<<ceil_div(p.D.M * p.ctot_f, 256), 256, 0, st>>>(rbf, p.nb_f, p.D.M * p.ctot_f, rdf);
+    reduce_slots_kernel<<<ceil_div(p.D.M * p.ctot_b, 256), 256, 0, st>>>(rbb, p.nb_b, p.D.M * p.ctot_b, rdb);
+    finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dx, p.ctot_f, rdf, ws.acc_f + p.Lf.scal_off(), to_dev(gp_f),
+                                               grad_flat + gl.f_P, grad_flat + gl.f_alpha, grad_flat + gl.f_S,
+                                               grad_flat + gl.f_Z, grad_flat + gl.f_ell, grad_flat + gl.f_sig2);
+    finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dh, p.ctot_b, rdb, ws.acc_b + p.Lb.scal_off(), to_dev(gp_b),
+                                               grad_flat + gl.b_P, grad_flat + gl.b_alpha, grad_flat + gl.b_S,
+                                               grad_flat + gl.b_Z, grad_flat + gl.b_ell, grad_flat + gl.b_sig2);
+    CBF_CUDA(cudaGetLastError());
+  } else {
   // reverse of the forward rollout (writes the y2 adjoints), then of the message chains
   const int grid_f = rev_grid(p, 2, p.ptiles);
   {
@@ -542,7 +713,6 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
                                                                   ws.acc_f);
   CBF_CUDA(cudaGetLastError());
 
-  const int nch = (int)p.chains.size();
   int nslots_b = 0;
   for (int c0 = 0; c0 < nch; c0 += kMaxChains) {
     ChainTable ct;
@@ -568,6 +738,7 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
   finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lb, ws.acc_b, to_dev(gp_b), grad_flat + gl.b_P, grad_flat + gl.b_alpha,
                                              grad_flat + gl.b_S, grad_flat + gl.b_Z, grad_flat + gl.b_ell,
                                              grad_flat + gl.b_sig2);
+  }
   finalize_noise_grad_kernel<<<1, 32 * ceil_div(p.dx, 32), 0, st>>>(
       p.dx, p.dy, p.din, ws.acc_f + p.Lf.scal_off(), ws.acc_b + p.Lb.scal_off(), ws.stats, var_y, (double)term_weights_host[0],
       (double)p.D.n_local * p.D.T, grad_flat + gl.var_x, grad_flat + gl.var_y);

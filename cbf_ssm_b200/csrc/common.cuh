@@ -22,6 +22,7 @@ struct Chain {
   int t_hi;
   int t_lo;
   int init;  // 0: h = 0 (cbfssm.py:106)   1: h = tile(z_b[run, t_hi]) (cbfssm.py:133-135)
+  int col0;  // number of live steps of all earlier chains (column block of the tensor-path operand matrices)
 };
 struct ChainTable {
   int count;
@@ -30,6 +31,13 @@ struct ChainTable {
 
 struct GpDev {
   const float *Z, *ell, *sig2, *P, *alpha, *S;
+};
+
+// Workspace views of the outer-product operand matrices one tensor-path reverse kernel writes
+// (float32, row-major [rows][L], L = live steps x particles): k', a_bar, a^2, w, g_mean, g_var, [x~,1].
+struct TcMats {
+  float *K, *Ab, *A2, *W, *Gm, *Gv, *X1;
+  size_t L;
 };
 
 // Device views into the caller's workspace.
@@ -110,7 +118,13 @@ struct DimOps {
                                cudaStream_t);
   cudaError_t (*fw_forward_tc)(const Dims &, GpDev, const float *vx, const float *vy, const float *u,
                                const float *y, const float *eps_f, Workspace, float *part_out, cudaStream_t);
-  size_t (*smem_tc)(int M, int which);     // which: 0 bm_fwd 1 fw_fwd
+  cudaError_t (*fw_reverse_tc)(const Dims &, GpDev, const float *vx, const float *vy, const float *u,
+                               const float *y, const float *eps_f, float w_ll, float w_kl, Workspace, TcMats,
+                               float *spart, int nsc, cudaStream_t);
+  cudaError_t (*bm_reverse_tc)(const Dims &, const ChainTable &, GpDev, const float *vx, const float *u,
+                               const float *y, const float *eps_b, const float *z_b, float w_en, Workspace,
+                               TcMats, float *spart, int nsc, cudaStream_t);
+  size_t (*smem_tc)(int M, int which);     // which: 0 bm_fwd 1 fw_fwd 2 fw_rev 3 bm_rev
   size_t (*smem_bytes)(int M, int which);  // which: 0 bm_fwd 1 fw_fwd 2 fw_rev 3 bm_rev
   int (*occupancy)(int M, int which);      // resident CTAs/SM of the persistent reverse kernels
   void (*layouts)(int M, AccLayout *Lf, AccLayout *Lb);   // accumulator layouts of the two reverse kernels

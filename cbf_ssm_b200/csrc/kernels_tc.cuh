@@ -13,7 +13,14 @@
 //   * every thread reads its accumulator row back with tcgen05.ld (16 columns at a time) and
 //     forms k.a and sum_m a_m^2 S_md in fp32 (SIMT), re-reading its own k' row from K1/K2.
 // The O(M.D) work stays on the SIMT pipes; only the 2 M^2 FLOPs per evaluation move to the tensor
-// pipe.  Reverse-mode kernels for large M still use the cooperative path.
+// pipe.
+//
+// Reverse mode (fw_reverse_tc / bm_reverse_tc): the same tile does, per step, the recomputation
+// a = P k and the second contraction P b on the tensor core (b is scaled per particle by a power
+// of two into fp16 range and split the same way), the step adjoint and the k_bar / x_bar chain in
+// SIMT, and writes the operands of the parameter-adjoint outer products (a_bar, k, a^2, w, g_mean,
+// g_var, x~) as float32 rows [m][step*particle] to the workspace; the accumulation over (particle,
+// step) is then a plain GEMM (cuBLAS SGEMM in column chunks, float64 across chunks; api.cu).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -88,20 +95,22 @@ __device__ __forceinline__ void split_h(float x, __half &h1, __half &h2) {
 }
 
 // Shared-memory state of one CTA: operands, resident small GP tables, barrier, TMEM base.
-template <int DIN, int DOUT>
+template <int DIN, int DOUT, bool REV = false>
 struct TcCtx {
   static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
-  __half *P1, *P2, *K1, *K2;
+  static constexpr uint32_t TMEM_COLS = REV ? 256u : 128u;
+  __half *P1, *P2, *K1, *K2, *B1, *B2;
   const float *Zt, *al, *Sm, *il;
   uint32_t bar, tmem, idesc;
   uint32_t phase;
   int M, MP;
   float sig2, pscale;   // P = pscale * P'
+  float smax[DOUT];     // max_m S_md (bound used to scale b in the reverse pass)
 
   static size_t bytes(int M) {
     const int MP = round_up(M, 16);
-    return (size_t)2 * MP * MP * 2 + (size_t)2 * kTcThreads * MP * 2 + sizeof(float) * ((size_t)M * (DINP + 2 * DOUTP) + DINP + 4) +
-           64;
+    return (size_t)2 * MP * MP * 2 + (size_t)2 * kTcThreads * MP * 2 +
+           sizeof(float) * ((size_t)M * (DINP + 2 * DOUTP) + DINP + 4) + 64;
   }
 
   // Carve + fill (all threads).  Allocates TMEM (warp 0) and initialises the mbarrier.
@@ -111,6 +120,9 @@ struct TcCtx {
     P2 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
     K1 = reinterpret_cast<__half *>(base); base += (size_t)kTcThreads * MP * 2;
     K2 = reinterpret_cast<__half *>(base); base += (size_t)kTcThreads * MP * 2;
+    // The reverse pass reuses the K operand buffers for b (k is re-read from the float32 operand
+    // matrix it was just written to, an L2 hit), which keeps the CTA at ~114 KB: two CTAs per SM.
+    B1 = K1; B2 = K2;
     float *Zw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DINP;
     float *aw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
     float *Sw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
@@ -153,6 +165,13 @@ struct TcCtx {
     for (int i = tid; i < DINP; i += nt) iw[i] = (i < DIN) ? 1.f / g.ell[i] : 0.f;
     Zt = Zw; al = aw; Sm = Sw; il = iw;
     sig2 = g.sig2[0];
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) smax[d] = 0.f;
+    if (REV) {
+      for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) smax[d] = fmaxf(smax[d], g.S[m * DOUT + d]);
+    }
     bar = smem_u32(barp);
     idesc = umma_idesc_f16(128, MP);
     phase = 0;
@@ -161,8 +180,8 @@ struct TcCtx {
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if (tid < 32) {   // one warp allocates 128 TMEM columns (fp32 accumulator 128 lanes x MP <= 128)
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemp)), "r"(128u)
+    if (tid < 32) {   // one warp allocates the TMEM columns (fp32 accumulators, 128 lanes x MP <= 128 each)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemp)), "r"(TMEM_COLS)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -178,17 +197,75 @@ struct TcCtx {
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
 };
 
+// D[tmem_d] = A1 P1 + A2 P1 + A1 P2 for the CTA's 128 rows; all threads call (contains the CTA barrier
+// and the mbarrier wait).  a1/a2: fp16 split A operands written by the threads just before.
+template <class Ctx>
+__device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __half *a2p, uint32_t tmem_d) {
+  async_proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    const uint32_t lboA = kTcThreads * 16, lboB = c.MP * 16;
+    const uint32_t a1 = smem_u32(a1p), a2 = smem_u32(a2p), b1 = smem_u32(c.P1), b2 = smem_u32(c.P2);
+    const int ks = c.MP / 16;
+    uint32_t acc = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t ab = (pass == 1) ? a2 : a1, bb = (pass == 2) ? b2 : b1;
+      for (int k = 0; k < ks; ++k) {
+        umma_f16(tmem_d, umma_desc(ab + k * 2 * lboA, lboA, 128), umma_desc(bb + k * 2 * lboB, lboB, 128), c.idesc, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(c.bar);
+  }
+  mbar_wait(c.bar, c.phase);
+  c.phase ^= 1;
+  tc_fence_after();
+}
+
+// This thread's row (16 fp16-split values starting at column 16*cc) of an A-operand buffer pair.
+__device__ __forceinline__ void tc_read_row16(const __half *b1, const __half *b2, int cc, float (&v)[16]) {
+#pragma unroll
+  for (int hch = 0; hch < 2; ++hch) {
+    const size_t off = (size_t)(cc * 2 + hch) * (kTcThreads * 8) + threadIdx.x * 8;
+    const uint4 v1 = *reinterpret_cast<const uint4 *>(b1 + off);
+    const uint4 v2 = *reinterpret_cast<const uint4 *>(b2 + off);
+    const uint32_t w1[4] = {v1.x, v1.y, v1.z, v1.w}, w2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w1[e]));
+      const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w2[e]));
+      v[hch * 8 + 2 * e] = f1.x + f2.x;
+      v[hch * 8 + 2 * e + 1] = f1.y + f2.y;
+    }
+  }
+}
+__device__ __forceinline__ void tc_write_row8(__half *b1, __half *b2, int ch, const float (&v)[8]) {
+  __half h1[8], h2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_h(v[e], h1[e], h2[e]);
+  const uint4 v1 = make_uint4(pack_h2(h1[0], h1[1]), pack_h2(h1[2], h1[3]), pack_h2(h1[4], h1[5]), pack_h2(h1[6], h1[7]));
+  const uint4 v2 = make_uint4(pack_h2(h2[0], h2[1]), pack_h2(h2[2], h2[3]), pack_h2(h2[4], h2[5]), pack_h2(h2[6], h2[7]));
+  const size_t off = (size_t)ch * (kTcThreads * 8) + threadIdx.x * 8;
+  *reinterpret_cast<uint4 *>(b1 + off) = v1;
+  *reinterpret_cast<uint4 *>(b2 + off) = v2;
+}
+
 // One sparse-GP evaluation (gp_tf.py:132-161) for the CTA's 128 particles; every thread must call.
-template <int DIN, int DOUT>
-__device__ __forceinline__ void gp_forward_tc(TcCtx<DIN, DOUT> &c, const float (&xin)[DIN], float (&fm)[DOUT],
-                                              float (&fv)[DOUT]) {
-  constexpr int DINP = TcCtx<DIN, DOUT>::DINP, DOUTP = TcCtx<DIN, DOUT>::DOUTP;
+// kout (optional): float32 matrix row pointer [m][ldk] receiving k' for the outer-product GEMMs.
+// amax: max_m |a''_m| of this particle's normalised accumulator row (scales b in the reverse pass);
+// kscale: the particle's normalisation, k' = kscale * k''.
+template <class Ctx, int DIN, int DOUT>
+__device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], float (&xt)[(DIN + 3) / 4 * 4],
+                                              float (&fm)[DOUT], float (&fv)[DOUT], float *__restrict__ kout,
+                                              size_t ldk, float &amax, float &kscale) {
+  constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   const int t = threadIdx.x, M = c.M, MP = c.MP;
-  float xt[DINP];
   {
     float il[DINP];
     ld_row<DINP>(c.il, il);
@@ -198,81 +275,71 @@ __device__ __forceinline__ void gp_forward_tc(TcCtx<DIN, DOUT> &c, const float (
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) fm[d] = 0.f;
   // ---- kernel vector -> fp16 split operands ----
+  // fp16 has a narrow exponent range and k' = exp(-d^2/2) can be 1e-12 for every inducing point (e.g.
+  // 21 input dims), so each particle's vector is normalised by its own maximum: pass 1 parks the squared
+  // distances (float32) in the thread's own K1/K2 slots and finds their minimum, pass 2 forms
+  // k'' = exp(-(d^2 - d^2_min)/2) in (0,1] (max exactly 1), splits and overwrites.  k' = kscale * k''.
+  float d2min = 3.0e38f;
   for (int ch = 0; ch < MP / 8; ++ch) {
-    __half h1[8], h2[8];
+    float dv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int m = ch * 8 + e;
+      float d2 = 3.0e38f;
+      if (m < M) {
+        float z[DINP];
+        ld_row<DINP>(c.Zt + m * DINP, z);
+        d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < DIN; ++j) { const float dl = xt[j] - z[j]; d2 = fmaf(dl, dl, d2); }
+        d2min = fminf(d2min, d2);
+      }
+      dv[e] = d2;
+    }
+    const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
+    *reinterpret_cast<float4 *>(c.K1 + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    *reinterpret_cast<float4 *>(c.K2 + off) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+  }
+  kscale = fast_exp2(kNegHalfLog2e * d2min);
+  for (int ch = 0; ch < MP / 8; ++ch) {
+    const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
+    const float4 da = *reinterpret_cast<const float4 *>(c.K1 + off), db = *reinterpret_cast<const float4 *>(c.K2 + off);
+    const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+    float kv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int m = ch * 8 + e;
       float kp = 0.f;
       if (m < M) {
-        float z[DINP];
-        ld_row<DINP>(c.Zt + m * DINP, z);
-        float d2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < DIN; ++j) { const float dl = xt[j] - z[j]; d2 = fmaf(dl, dl, d2); }
-        kp = fast_exp2(kNegHalfLog2e * d2);
+        kp = fast_exp2(kNegHalfLog2e * (dv[e] - d2min));
         float al[DOUTP];
         ld_row<DOUTP>(c.al + m * DOUTP, al);
 #pragma unroll
         for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(kp, al[d], fm[d]);
+        if (kout) kout[(size_t)m * ldk] = kscale * kp;
       }
-      split_h(kp, h1[e], h2[e]);
+      kv[e] = kp;
     }
-    const uint4 v1 = make_uint4(pack_h2(h1[0], h1[1]), pack_h2(h1[2], h1[3]), pack_h2(h1[4], h1[5]), pack_h2(h1[6], h1[7]));
-    const uint4 v2 = make_uint4(pack_h2(h2[0], h2[1]), pack_h2(h2[2], h2[3]), pack_h2(h2[4], h2[5]), pack_h2(h2[6], h2[7]));
-    *reinterpret_cast<uint4 *>(c.K1 + (size_t)ch * (kTcThreads * 8) + t * 8) = v1;
-    *reinterpret_cast<uint4 *>(c.K2 + (size_t)ch * (kTcThreads * 8) + t * 8) = v2;
+    tc_write_row8(c.K1, c.K2, ch, kv);
   }
-  // ---- D = K1 P1 + K2 P1 + K1 P2 on the tensor core ----
-  async_proxy_fence();
-  tc_fence_before();
-  __syncthreads();
-  if (t == 0) {
-    tc_fence_after();
-    const uint32_t lboA = kTcThreads * 16, lboB = MP * 16;
-    const uint32_t a1 = smem_u32(c.K1), a2 = smem_u32(c.K2), b1 = smem_u32(c.P1), b2 = smem_u32(c.P2);
-    const int ks = MP / 16;
-    uint32_t acc = 0;
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t ab = (pass == 1) ? a2 : a1, bb = (pass == 2) ? b2 : b1;
-      for (int k = 0; k < ks; ++k) {
-        umma_f16(c.tmem, umma_desc(ab + k * 2 * lboA, lboA, 128), umma_desc(bb + k * 2 * lboB, lboB, 128), c.idesc, acc);
-        acc = 1;
-      }
-    }
-    umma_commit(c.bar);
-  }
-  mbar_wait(c.bar, c.phase);
-  c.phase ^= 1;
-  tc_fence_after();
+  // ---- D1 = K P' on the tensor core ----
+  tc_contract(c, c.K1, c.K2, c.tmem);
   // ---- accumulator row back: q' = k'.a', v'_d = sum a'^2 S ----
   float q = 0.f;
+  amax = 0.f;
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
   for (int cc = 0; cc < MP / 16; ++cc) {
-    float a[16];
+    float a[16], kp[16];
     tmem_ld16(trow + cc * 16, a);
-    float kp[16];
-#pragma unroll
-    for (int hch = 0; hch < 2; ++hch) {
-      const size_t off = (size_t)(cc * 2 + hch) * (kTcThreads * 8) + t * 8;
-      const uint4 v1 = *reinterpret_cast<const uint4 *>(c.K1 + off);
-      const uint4 v2 = *reinterpret_cast<const uint4 *>(c.K2 + off);
-      const uint32_t w1[4] = {v1.x, v1.y, v1.z, v1.w}, w2[4] = {v2.x, v2.y, v2.z, v2.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w1[e]));
-        const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w2[e]));
-        kp[hch * 8 + 2 * e] = f1.x + f2.x;
-        kp[hch * 8 + 2 * e + 1] = f1.y + f2.y;
-      }
-    }
+    tc_read_row16(c.K1, c.K2, cc, kp);
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
       if (m < M) {
         q = fmaf(kp[e], a[e], q);
+        amax = fmaxf(amax, fabsf(a[e]));
         const float a2 = a[e] * a[e];
         float S[DOUTP];
         ld_row<DOUTP>(c.Sm + m * DOUTP, S);
@@ -281,13 +348,126 @@ __device__ __forceinline__ void gp_forward_tc(TcCtx<DIN, DOUT> &c, const float (
       }
     }
   }
-  const float s4 = c.sig2 * c.sig2, ps = c.pscale;
+  // q, fv, amax were formed from the normalised k'' and a'' = P' k''; undo the per-particle scale
+  const float s4 = c.sig2 * c.sig2, ps = c.pscale, k2 = kscale * kscale;
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) {
-    fm[d] *= c.sig2;
-    fv[d] = c.sig2 - ps * s4 * q + ps * ps * s4 * fv[d];
+    fm[d] *= c.sig2 * kscale;
+    fv[d] = c.sig2 - ps * s4 * k2 * q + ps * ps * s4 * k2 * fv[d];
   }
-  tc_fence_before();   // order this step's tcgen05.ld before the next step's barrier / MMA
+  tc_fence_before();   // order this step's tcgen05.ld before the next barrier / MMA
+}
+
+// Destination rows (float32, [row][ld], this particle's column already applied) of the
+// outer-product operands one reverse evaluation writes.
+struct TcOut {
+  float *K, *Ab, *A2, *W, *Gm, *Gv, *X1;
+  size_t ld;
+};
+
+// Reverse of one GP evaluation (SURVEY 8a note 4) on the tile; follows gp_forward_tc of the same step
+// (K1/K2 and the accumulator D1 still hold k' and a').  gm/gv: adjoints of (fmean, fvar).
+template <class Ctx, int DIN, int DOUT, int NEED>
+__device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3) / 4 * 4], const float (&gm)[DOUT],
+                                              const float (&gv)[DOUT], float amax, float kscale, bool live,
+                                              const TcOut &o, float (&xinb)[NEED], float (&Lacc)[DIN], float &sw,
+                                              float &sG) {
+  constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
+  const int t = threadIdx.x, M = c.M, MP = c.MP;
+  const float ps = c.pscale, sig2 = c.sig2;
+  const float ascale = ps * sig2 * kscale;      // a = ascale * a'' (a'' = P' k'' is what D1 holds)
+  float Gs = 0.f, cbound = 0.f;
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) { Gs += gv[d]; cbound += fabsf(gv[d]) * c.smax[d]; }
+  sG += Gs;
+  // per-particle power-of-two scale so that |b''| = |a'' c| * 2^-e <= 1  (amax is of the normalised a'')
+  int e2 = 0;
+  frexpf(fmaxf(amax * cbound, 1e-30f), &e2);
+  const float bsc = ldexpf(1.f, -e2), binv = ldexpf(1.f, e2);
+  const uint32_t trow1 = c.tmem + ((uint32_t)(t & ~31) << 16), trow2 = trow1 + 128;
+  if (live) {
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) { o.Gm[(size_t)d * o.ld] = gm[d]; o.Gv[(size_t)d * o.ld] = gv[d]; }
+#pragma unroll
+    for (int j = 0; j < DIN; ++j) o.X1[(size_t)j * o.ld] = xt[j];
+    o.X1[(size_t)DIN * o.ld] = 1.f;
+  }
+  // ---- b'' = a' (S gv) 2^-e -> fp16 split rows of B ----
+  for (int cc = 0; cc < MP / 16; ++cc) {
+    float a[16];
+    tmem_ld16(trow1 + cc * 16, a);
+    float bv[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int m = cc * 16 + e;
+      float b = 0.f;
+      if (m < M) {
+        float S[DOUTP];
+        ld_row<DOUTP>(c.Sm + m * DOUTP, S);
+        float cm = 0.f;
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], gv[d], cm);
+        b = a[e] * cm * bsc;
+        if (live) { const float at = ascale * a[e]; o.A2[(size_t)m * o.ld] = at * at; }
+      }
+      bv[e] = b;
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { lo[e] = bv[e]; hi[e] = bv[8 + e]; }
+    tc_write_row8(c.B1, c.B2, 2 * cc, lo);
+    tc_write_row8(c.B1, c.B2, 2 * cc + 1, hi);
+  }
+  tc_fence_before();
+  // ---- D2 = B P' ----
+  tc_contract(c, c.B1, c.B2, c.tmem + 128);
+  // ---- k_bar = alpha gm + 2 P b - 2 G a ; w = k_bar k ; a_bar = 2 b - G k ----
+  const float pbs = ps * ascale * binv;         // (P b)_m = pbs * (P' b'')_m
+  const float bs = ascale * binv;               // b_m = bs * b''_m
+#pragma unroll
+  for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
+  for (int cc = 0; cc < MP / 16; ++cc) {
+    float pb[16], a[16], kp[16], bb[16];
+    tmem_ld16(trow2 + cc * 16, pb);
+    tmem_ld16(trow1 + cc * 16, a);
+    tc_read_row16(c.B1, c.B2, cc, bb);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) kp[e] = (live && cc * 16 + e < M) ? o.K[(size_t)(cc * 16 + e) * o.ld] : 0.f;   // true k'
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int m = cc * 16 + e;
+      if (m < M) {
+        float al[DOUTP];
+        ld_row<DOUTP>(c.al + m * DOUTP, al);
+        float kb = 2.f * pbs * pb[e] - 2.f * Gs * ascale * a[e];
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gm[d], kb);
+        const float k = sig2 * kp[e];
+        const float w = kb * k;
+        sw += w;
+        float z[DINP];
+        ld_row<DINP>(c.Zt + m * DINP, z);
+#pragma unroll
+        for (int j = 0; j < DIN; ++j) {
+          const float dl = xt[j] - z[j];
+          const float wd = w * dl;
+          if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
+          Lacc[j] = fmaf(wd, dl, Lacc[j]);
+        }
+        if (live) {
+          o.W[(size_t)m * o.ld] = w;
+          o.Ab[(size_t)m * o.ld] = 2.f * bs * bb[e] - Gs * k;
+        }
+      }
+    }
+  }
+  {
+    float il[DINP];
+    ld_row<DINP>(c.il, il);
+#pragma unroll
+    for (int j = 0; j < NEED; ++j) xinb[j] *= il[j];
+  }
+  tc_fence_before();
 }
 
 // =====================================================================================
@@ -333,7 +513,8 @@ __global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, Chain
 #pragma unroll
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
-    gp_forward_tc<DIN, DH>(c, xin, fm, fv);
+    float xt[TcCtx<DIN, DH>::DINP], amax, kscale;
+    gp_forward_tc<TcCtx<DIN, DH>, DIN, DH>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
     const bool write = writer_run(t, D.R) == ch.run;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
@@ -405,7 +586,8 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
     for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
     load_ytil(t + 1, yt);
     const float e = eps_f[(size_t)t * D.n_local + nr];
-    gp_forward_tc<DIN, DX>(c, xin, fm, fv);
+    float xt[TcCtx<DIN, DX>::DINP], amax, kscale;
+    gp_forward_tc<TcCtx<DIN, DX>, DIN, DX>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
     const bool do_cond = D.condition || (t < D.R - 1);
     fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, xn, kl);
 #pragma unroll
@@ -420,11 +602,229 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
   cta_sum_store<DY + 1>(sse, scratch, part_out + (size_t)blockIdx.x * (DY + 1));
 }
 
+__device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
+  TcOut o;
+  o.K = m.K + col; o.Ab = m.Ab + col; o.A2 = m.A2 + col; o.W = m.W + col;
+  o.Gm = m.Gm + col; o.Gv = m.Gv + col; o.X1 = m.X1 + col;
+  o.ld = m.L;
+  return o;
+}
+
+// =====================================================================================
+// Reverse of the forward rollout on tcgen05: one CTA = 128 particles, T-1 steps.
+// Per-CTA output: scalar sums [L_j | sum w | sum G | var_x_bar | var_y_bar] at spart[cta].
+// =====================================================================================
+template <int DX, int DU, int DY>
+__global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+                                                                   const float *__restrict__ vyg,
+                                                                   const float *__restrict__ u,
+                                                                   const float *__restrict__ y,
+                                                                   const float *__restrict__ eps_f, float w_ll,
+                                                                   float w_kl, Workspace ws, TcMats mats,
+                                                                   float *__restrict__ spart, int nsc) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  using Ctx = TcCtx<DIN, DX, true>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float scratch[4 * (DIN + 2 + 2 * DX)];
+  __shared__ float vx[16], vy[16];
+  Ctx c;
+  c.init(smem_raw, gp, D.M, scratch);
+  if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
+  __syncthreads();
+
+  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const bool live = nl < D.n_local;
+  const int nr = live ? nl : 0;
+  const int b = (D.n_offset + nr) / D.S;
+  const float *ub = u + (size_t)b * D.T * DU;
+  const float *yb = y + (size_t)b * D.T * DY;
+  const size_t np = ws.npad;
+
+  float Lacc[DIN], sw = 0.f, sG = 0.f, vxacc[DX], vyacc[DX];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) Lacc[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < DX; ++j) { vxacc[j] = 0.f; vyacc[j] = 0.f; }
+
+  float xb[DX];
+  {
+    const float *Xp = ws.X + ((size_t)(D.T - 1) * DX) * np + nr;
+#pragma unroll
+    for (int j = 0; j < DX; ++j)
+      xb[j] = (j < DY && live) ? w_ll * (yb[(D.T - 1) * DY + (j < DY ? j : 0)] - Xp[j * np]) / vy[j] : 0.f;
+  }
+#pragma unroll 1
+  for (int t = D.T - 2; t >= 0; --t) {
+    float x[DX], xin[DIN], xt[Ctx::DINP], fm[DX], fv[DX], yt[DX], amax, kscale;
+    const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
+#pragma unroll
+    for (int j = 0; j < DX; ++j) { x[j] = Xp[j * np]; xin[j] = x[j]; }
+#pragma unroll
+    for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
+#pragma unroll
+    for (int j = 0; j < DY; ++j) yt[j] = yb[(t + 1) * DY + j];
+    {
+      const float *Hp = ws.H + (((size_t)writer_run(t + 1, D.R) * D.T + (t + 1)) * DH) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) yt[DY + j] = Hp[j * np];
+    }
+    const float e = eps_f[(size_t)t * D.n_local + nr];
+    const TcOut o = tc_out_at(mats, (size_t)t * D.n_local + nr);
+    gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? o.K : nullptr, o.ld, amax, kscale);
+    const bool do_cond = D.condition || (t < D.R - 1);
+    float fmb[DX], fvb[DX], ytb[DX];
+    fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
+    if (live) {
+      float *Yp = ws.Yb + ((size_t)(t + 1) * DH) * np + nl;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) Yp[j * np] = ytb[DY + j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < DX; ++j) { fmb[j] = 0.f; fvb[j] = 0.f; }
+    }
+    float xinb[DX];
+    gp_reverse_tc<Ctx, DIN, DX, DX>(c, xt, fmb, fvb, amax, kscale, live, o, xinb, Lacc, sw, sG);
+#pragma unroll
+    for (int j = 0; j < DX; ++j) {
+      float lg = 0.f;
+      if (j < DY && live) lg = w_ll * (yb[t * DY + (j < DY ? j : 0)] - x[j]) / vy[j];
+      xb[j] = xinb[j] + fmb[j] + lg;
+    }
+  }
+  if (live) {
+    float *Yp = ws.Yb + nl;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) Yp[j * np] = xb[DY + j];
+  }
+  c.release();
+  float sc[DIN + 2 + 2 * DX];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) sc[j] = Lacc[j];
+  sc[DIN] = sw; sc[DIN + 1] = sG;
+#pragma unroll
+  for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = vxacc[j]; sc[DIN + 2 + DX + j] = vyacc[j]; }
+  cta_sum_store<DIN + 2 + 2 * DX>(sc, scratch, spart + (size_t)blockIdx.x * nsc);
+}
+
+template <int DX, int DU, int DY>
+__global__ void __launch_bounds__(kTcThreads) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+                                                                   const float *__restrict__ vxg,
+                                                                   const float *__restrict__ u,
+                                                                   const float *__restrict__ y,
+                                                                   const float *__restrict__ eps_b,
+                                                                   const float *__restrict__ z_b, float w_en,
+                                                                   Workspace ws, TcMats mats,
+                                                                   float *__restrict__ spart, int nsc) {
+  constexpr int DH = DX - DY, DIN = DX + DU;
+  using Ctx = TcCtx<DIN, DH, true>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float scratch[4 * (DIN + 2 + 2 * DX)];
+  __shared__ float vx[16];
+  Ctx c;
+  c.init(smem_raw, gp, D.M, scratch);
+  if (threadIdx.x < DX) vx[threadIdx.x] = vxg[threadIdx.x];
+  __syncthreads();
+
+  const Chain ch = chains.c[blockIdx.y];
+  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const bool live = nl < D.n_local;
+  const int nr = live ? nl : 0;
+  const int b = (D.n_offset + nr) / D.S;
+  const float *ub = u + (size_t)b * D.T * DU;
+  const float *yb = y + (size_t)b * D.T * DY;
+  const size_t np = ws.npad;
+
+  float Lacc[DIN], sw = 0.f, sG = 0.f, vxacc[DH];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) Lacc[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < DH; ++j) vxacc[j] = 0.f;
+
+  float hb[DH];
+#pragma unroll
+  for (int j = 0; j < DH; ++j) hb[j] = 0.f;
+#pragma unroll 1
+  for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
+    float hid[DH], xin[DIN], xt[Ctx::DINP], fm[DH], fv[DH], amax, kscale;
+    if (t == ch.t_hi) {
+      const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) hid[j] = z;
+    } else {
+      const float *Hp = ws.H + (((size_t)ch.run * D.T + (t + 1)) * DH) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) hid[j] = Hp[j * np];
+    }
+#pragma unroll
+    for (int j = 0; j < DH; ++j) xin[j] = hid[j];
+#pragma unroll
+    for (int j = 0; j < DU; ++j) xin[DH + j] = ub[t * DU + j];
+#pragma unroll
+    for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
+    const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
+    const TcOut o = tc_out_at(mats, ((size_t)ch.col0 + (t - ch.t_lo)) * D.n_local + nr);
+    gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, live ? o.K : nullptr, o.ld, amax, kscale);
+    const bool write = writer_run(t, D.R) == ch.run;
+    float ob[DH], fvb[DH];
+    const float *Yp = ws.Yb + ((size_t)t * DH) * np + nr;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) {
+      const float f = fv[j] + vx[j];
+      float ov = hb[j], fb = 0.f;
+      if (write) {
+        ov += Yp[j * np];
+        fb = w_en * 0.5f / f;
+      }
+      fb += ov * e * 0.5f * rsqrtf(f);
+      if (!live) { ov = 0.f; fb = 0.f; }
+      ob[j] = ov; fvb[j] = fb;
+      vxacc[j] += fb;
+    }
+    float xinb[DH];
+    gp_reverse_tc<Ctx, DIN, DH, DH>(c, xt, ob, fvb, amax, kscale, live, o, xinb, Lacc, sw, sG);
+#pragma unroll
+    for (int j = 0; j < DH; ++j) hb[j] = xinb[j] + ob[j];
+  }
+  c.release();
+  float sc[DIN + 2 + 2 * DX];
+#pragma unroll
+  for (int j = 0; j < DIN; ++j) sc[j] = Lacc[j];
+  sc[DIN] = sw; sc[DIN + 1] = sG;
+#pragma unroll
+  for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = (j < DH) ? vxacc[j < DH ? j : 0] : 0.f; sc[DIN + 2 + DX + j] = 0.f; }
+  cta_sum_store<DIN + 2 + 2 * DX>(sc, scratch, spart + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nsc);
+}
+
 template <int DX, int DU, int DY>
 struct LaunchTc {
   static constexpr int DH = DX - DY, DIN = DX + DU;
   static size_t smem_b(int M) { return TcCtx<DIN, DH>::bytes(M); }
   static size_t smem_f(int M) { return TcCtx<DIN, DX>::bytes(M); }
+  static size_t smem_rb(int M) { return TcCtx<DIN, DH, true>::bytes(M); }
+  static size_t smem_rf(int M) { return TcCtx<DIN, DX, true>::bytes(M); }
+
+  static cudaError_t fw_reverse(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
+                                const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
+                                TcMats mats, float *spart, int nsc, cudaStream_t st) {
+    const size_t smem = smem_rf(D.M);
+    cudaError_t e = cudaFuncSetAttribute(fw_reverse_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fw_reverse_tc_kernel<DX, DU, DY><<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(
+        D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, spart, nsc);
+    return cudaGetLastError();
+  }
+  static cudaError_t bm_reverse(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
+                                const float *y, const float *eps_b, const float *z_b, float w_en, Workspace ws,
+                                TcMats mats, float *spart, int nsc, cudaStream_t st) {
+    if (ct.count == 0) return cudaSuccess;
+    const size_t smem = smem_rb(D.M);
+    cudaError_t e = cudaFuncSetAttribute(bm_reverse_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(ceil_div(D.n_local, kTcThreads), ct.count);
+    bm_reverse_tc_kernel<DX, DU, DY><<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats,
+                                                                    spart, nsc);
+    return cudaGetLastError();
+  }
 
   static cudaError_t bm_forward(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
                                 const float *y, const float *eps_b, const float *z_b, Workspace ws,

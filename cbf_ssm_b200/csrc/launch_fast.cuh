@@ -123,6 +123,8 @@ DimOps make_fast_ops() {
   o.bm_reverse = &L::bm_reverse;
   o.bm_forward_tc = nullptr;
   o.fw_forward_tc = nullptr;
+  o.fw_reverse_tc = nullptr;
+  o.bm_reverse_tc = nullptr;
   o.smem_tc = nullptr;
   o.smem_bytes = &L::smem_bytes;
   o.occupancy = &L::occupancy;

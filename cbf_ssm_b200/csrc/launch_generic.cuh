@@ -118,7 +118,12 @@ DimOps make_ops() {
   o.bm_reverse = &Launch<DX, DU, DY>::bm_reverse;
   o.bm_forward_tc = &LaunchTc<DX, DU, DY>::bm_forward;
   o.fw_forward_tc = &LaunchTc<DX, DU, DY>::fw_forward;
-  o.smem_tc = [](int M, int which) { return which == 0 ? LaunchTc<DX, DU, DY>::smem_b(M) : LaunchTc<DX, DU, DY>::smem_f(M); };
+  o.fw_reverse_tc = &LaunchTc<DX, DU, DY>::fw_reverse;
+  o.bm_reverse_tc = &LaunchTc<DX, DU, DY>::bm_reverse;
+  o.smem_tc = [](int M, int which) {
+    using L = LaunchTc<DX, DU, DY>;
+    return which == 0 ? L::smem_b(M) : which == 1 ? L::smem_f(M) : which == 2 ? L::smem_rf(M) : L::smem_rb(M);
+  };
   o.smem_bytes = &Launch<DX, DU, DY>::smem_bytes;
   o.occupancy = &Launch<DX, DU, DY>::occupancy;
   o.layouts = &Launch<DX, DU, DY>::layouts;
