@@ -253,8 +253,8 @@ def run_b200(args):
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = eng.launches
     clocks = sampler.stop() if rank == 0 else None
-    kms = (ctypes.c_double * 4)()
-    kcnt = (ctypes.c_int64 * 4)()
+    kms = (ctypes.c_double * 8)()
+    kcnt = (ctypes.c_int64 * 8)()
     _lib.check(lib.cbf_timing_read(kms, kcnt))
     lib.cbf_timing_enable(0)
     ms_per_step = ms_total / args.steps
@@ -300,7 +300,8 @@ def run_b200(args):
                 "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({how} MEASURED_PEAKS.json); the path is FP32-SIMT "
                                "compute-bound (SURVEY 8d), not HBM- or tensor-bound",
                 "flops_per_particle_step": {k: v for k, v in zip(knames, kflops)},
-                "kernel_ms_avg": {k: v for k, v in zip(knames, kavg)},
+                "kernel_ms_avg": {**{k: v for k, v in zip(knames, kavg)},
+                                  **({"outer_f": kms[4] / kcnt[4], "outer_b": kms[5] / kcnt[5]} if kcnt[4] else {})},
                 "kernel_share_of_step": {k: (kms[i] / max(kcnt[i], 1)) * (kcnt[i] / args.steps) / ms_per_step
                                          for i, k in enumerate(knames)},
                 "whole_step_frac": step_frac,

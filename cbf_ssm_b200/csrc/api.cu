@@ -4,10 +4,9 @@
 #include <string.h>
 #include <vector>
 
-#include <cublas_v2.h>
-
 #include "common.cuh"
 #include "dims_list.h"
+#include "kernels_outer.cuh"
 
 namespace cbf {
 
@@ -46,7 +45,7 @@ const DimOps *find_ops(int dx, int du, int dy, int M, bool allow_fast) {
 struct TimingPool {
   bool enabled = false;
   std::vector<cudaEvent_t> ev;      // pairs (start, stop)
-  std::vector<int> kind;            // 0 bm_forward 1 fw_forward 2 fw_reverse 3 bm_reverse
+  std::vector<int> kind;            // 0 bm_forward 1 fw_forward 2 fw_reverse 3 bm_reverse 4/5 outer-product accumulation f/b
   size_t used = 0;
 };
 static thread_local TimingPool g_timing;
@@ -111,13 +110,13 @@ struct Plan {
   // tensor-core path (48 <= M <= 128, enough particles)
   bool tc_fwd, tc_rev;
   size_t colsf, colsb;           // columns (live steps x particles) of the operand matrices
-  int ctot_f, ctot_b, nb_f, nb_b, nsc_f, nsc_b, nspart_f, nspart_b;
-  size_t off_mf, off_mb, off_spf, off_spb, off_rbf, off_rbb, off_rdf, off_rdb, off_blas;
+  size_t off_rpart;              // per-CTA float64 partials of the tcgen05 outer-product kernel
+  int ctot_f, ctot_b, nsc_f, nsc_b, nspart_f, nspart_b;
+  size_t off_mf, off_mb, off_spf, off_spb, off_rdf, off_rdb;
 };
 
-constexpr size_t kTcChunk = 32768;              // columns per SGEMM (float32 inside, float64 across)
-constexpr size_t kBlasWorkspace = 32u << 20;
 constexpr size_t kTcMaxMatBytes = (size_t)96 << 30;
+constexpr int kOuterMaxGrid = 148 * 2;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -189,45 +188,56 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
     p.ctot_f = s->M + 2 * p.dx + p.din + 1;
     p.ctot_b = s->M + 2 * p.dh + p.din + 1;
     const size_t rows_f = (size_t)4 * s->M + 2 * p.dx + p.din + 1, rows_b = (size_t)4 * s->M + 2 * p.dh + p.din + 1;
-    const size_t bytes = sizeof(float) * (rows_f * p.colsf + rows_b * p.colsb);
+    const size_t blkf = (p.colsf + 15) / 16, blkb = (p.colsb + 15) / 16;
+    const size_t bytes = sizeof(float) * 16 * (rows_f * blkf + rows_b * blkb);
     p.tc_rev = p.tc_fwd && p.ops->fw_reverse_tc != nullptr && p.ops->smem_tc(s->M, 2) <= kMaxSmem &&
                p.ops->smem_tc(s->M, 3) <= kMaxSmem && bytes <= kTcMaxMatBytes && p.colsf > 0 && p.colsb > 0 &&
                p.colsf < ((size_t)1 << 31) && p.colsb < ((size_t)1 << 31);
     if (p.tc_rev) {
-      p.nb_f = (int)((p.colsf + kTcChunk - 1) / kTcChunk);
-      p.nb_b = (int)((p.colsb + kTcChunk - 1) / kTcChunk);
       p.nsc_f = p.Lf.slot() - p.Lf.scal_off();
       p.nsc_b = p.Lb.slot() - p.Lb.scal_off();
       const int pt = ceil_div(s->n_local, 128);
       p.nspart_f = pt;
       p.nspart_b = pt * (int)p.chains.size();
-      p.off_mf = o; o = align_up(o + sizeof(float) * rows_f * p.colsf, 256);
-      p.off_mb = o; o = align_up(o + sizeof(float) * rows_b * p.colsb, 256);
+      p.off_mf = o; o = align_up(o + sizeof(float) * 16 * rows_f * blkf, 256);
+      p.off_mb = o; o = align_up(o + sizeof(float) * 16 * rows_b * blkb, 256);
+      p.off_rpart = o; o = align_up(o + sizeof(double) * (size_t)kOuterMaxGrid * 128 * kOCols, 256);
       p.off_spf = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_f * p.nsc_f, 256);
       p.off_spb = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_b * p.nsc_b, 256);
-      p.off_rbf = o; o = align_up(o + sizeof(float) * (size_t)p.nb_f * s->M * p.ctot_f, 256);
-      p.off_rbb = o; o = align_up(o + sizeof(float) * (size_t)p.nb_b * s->M * p.ctot_b, 256);
       p.off_rdf = o; o = align_up(o + sizeof(double) * (size_t)s->M * p.ctot_f, 256);
       p.off_rdb = o; o = align_up(o + sizeof(double) * (size_t)s->M * p.ctot_b, 256);
-      p.off_blas = o; o = align_up(o + kBlasWorkspace, 256);
     }
   }
   p.total = o;
   return 0;
 }
 
+static int device_sms();
+
 static TcMats bind_mats(void *base, size_t off, size_t L, int M, int dout, int din) {
-  float *f = reinterpret_cast<float *>(static_cast<char *>(base) + off);
   TcMats m;
+  m.blk = reinterpret_cast<float *>(static_cast<char *>(base) + off);
   m.L = L;
-  m.K = f; f += (size_t)M * L;
-  m.Ab = f; f += (size_t)M * L;
-  m.A2 = f; f += (size_t)M * L;
-  m.W = f; f += (size_t)M * L;
-  m.Gm = f; f += (size_t)dout * L;
-  m.Gv = f; f += (size_t)dout * L;
-  m.X1 = f;
+  m.rAb = 0; m.rK = M; m.rA2 = 2 * M; m.rW = 3 * M;
+  m.rGm = 4 * M; m.rGv = 4 * M + dout; m.rX1 = 4 * M + 2 * dout;
+  m.R = 4 * M + 2 * dout + din + 1;
   return m;
+}
+
+// P_bar', alpha_bar', S_bar, [U|r] of one GP on the tensor cores (kernels_outer.cuh) -> Rd [M x Ctot] float64.
+static cudaError_t tc_outer(const TcMats &m, int M, int dout, int din, double *rpart, double *Rd, cudaStream_t st) {
+  OuterArgs a{m, M, dout, din};
+  const size_t ntile = (m.L + kOT - 1) / kOT;
+  int grid = device_sms();          // one CTA per SM: the 3-stage ring takes ~216 KB of shared memory
+  if (grid > kOuterMaxGrid) grid = kOuterMaxGrid;
+  if ((size_t)grid > ntile) grid = (int)ntile;
+  const size_t smem = outer_smem_bytes(din);
+  cudaError_t e = cudaFuncSetAttribute(tc_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc_outer_kernel<<<grid, kOThreads, smem, st>>>(a, rpart);
+  const int Ctot = M + 2 * dout + din + 1;
+  outer_reduce_kernel<<<ceil_div(M * Ctot, 256), 256, 0, st>>>(rpart, grid, M, dout, din, Rd);
+  return cudaGetLastError();
 }
 
 static Workspace bind_workspace(const Plan &p, void *base) {
@@ -517,47 +527,6 @@ static int check_gp(const cbf_gp *g, const char *name) {
   return 0;
 }
 
-static thread_local cublasHandle_t g_blas = nullptr;
-
-static const char *blas_status(cublasStatus_t st) {
-  switch (st) {
-    case CUBLAS_STATUS_SUCCESS: return "success";
-    case CUBLAS_STATUS_NOT_INITIALIZED: return "not initialized";
-    case CUBLAS_STATUS_ALLOC_FAILED: return "alloc failed";
-    case CUBLAS_STATUS_INVALID_VALUE: return "invalid value";
-    case CUBLAS_STATUS_EXECUTION_FAILED: return "execution failed";
-    default: return "error";
-  }
-}
-
-// R[nb][M x Ctot] (float32) <- chunked outer-product sums of one GP's operand matrices:
-// block (left, right, C) at column c0: R[:, c0:c0+C] = left[M x L] . right[C x L]^T, one SGEMM per chunk of
-// kTcChunk columns (float32 accumulation inside a chunk only).
-static int tc_gemms(cublasHandle_t h, const TcMats &m, int M, int dout, int din, int Ctot, float *R) {
-  const float one = 1.f, zero = 0.f;
-  const size_t L = m.L, nfull = L / kTcChunk, rem = L - nfull * kTcChunk;
-  const float *left[4] = {m.Ab, m.K, m.A2, m.W};
-  const float *right[4] = {m.K, m.Gm, m.Gv, m.X1};
-  const int C[4] = {M, dout, dout, din + 1};
-  int c0 = 0;
-  for (int b = 0; b < 4; ++b) {
-    cublasStatus_t st = CUBLAS_STATUS_SUCCESS;
-    if (nfull > 0)
-      st = cublasSgemmStridedBatched(h, CUBLAS_OP_T, CUBLAS_OP_N, C[b], M, (int)kTcChunk, &one, right[b], (int)L,
-                                     (long long)kTcChunk, left[b], (int)L, (long long)kTcChunk, &zero, R + c0, Ctot,
-                                     (long long)M * Ctot, (int)nfull);
-    if (st == CUBLAS_STATUS_SUCCESS && rem > 0)
-      st = cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, C[b], M, (int)rem, &one, right[b] + nfull * kTcChunk, (int)L,
-                       left[b] + nfull * kTcChunk, (int)L, &zero, R + nfull * (size_t)M * Ctot + c0, Ctot);
-    if (st != CUBLAS_STATUS_SUCCESS) {
-      set_error("cuBLAS SGEMM failed: %s", blas_status(st));
-      return 700 + (int)st;
-    }
-    c0 += C[b];
-  }
-  return 0;
-}
-
 #define CBF_CUDA(expr)                                                         \
   do {                                                                         \
     cudaError_t _e = (expr);                                                   \
@@ -666,7 +635,6 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
     const TcMats mf = bind_mats(workspace, p.off_mf, p.colsf, p.D.M, p.dx, p.din);
     const TcMats mb = bind_mats(workspace, p.off_mb, p.colsb, p.D.M, p.dh, p.din);
     float *spf = reinterpret_cast<float *>(wb + p.off_spf), *spb = reinterpret_cast<float *>(wb + p.off_spb);
-    float *rbf = reinterpret_cast<float *>(wb + p.off_rbf), *rbb = reinterpret_cast<float *>(wb + p.off_rbb);
     double *rdf = reinterpret_cast<double *>(wb + p.off_rdf), *rdb = reinterpret_cast<double *>(wb + p.off_rdb);
     {
       ScopedTiming tm(2, st);
@@ -684,17 +652,15 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
     reduce_slots_kernel<<<ceil_div(p.nsc_f, 256), 256, 0, st>>>(spf, p.nspart_f, p.nsc_f, ws.acc_f + p.Lf.scal_off());
     reduce_slots_kernel<<<ceil_div(p.nsc_b, 256), 256, 0, st>>>(spb, p.nspart_b, p.nsc_b, ws.acc_b + p.Lb.scal_off());
     CBF_CUDA(cudaGetLastError());
-    if (!g_blas) {
-      cublasStatus_t bs = cublasCreate(&g_blas);
-      if (bs != CUBLAS_STATUS_SUCCESS) { g_blas = nullptr; set_error("cublasCreate failed: %s", blas_status(bs)); return 700 + (int)bs; }
+    double *rpart = reinterpret_cast<double *>(wb + p.off_rpart);
+    {
+      ScopedTiming tm(4, st);
+      CBF_CUDA(tc_outer(mf, p.D.M, p.dx, p.din, rpart, rdf, st));
     }
-    cublasSetStream(g_blas, st);
-    cublasSetWorkspace(g_blas, wb + p.off_blas, kBlasWorkspace);
-    cublasSetMathMode(g_blas, CUBLAS_DEFAULT_MATH);       // SGEMM: float32 FMA accumulation (TF32 is opt-in only)
-    if ((rc = tc_gemms(g_blas, mf, p.D.M, p.dx, p.din, p.ctot_f, rbf))) return rc;
-    if ((rc = tc_gemms(g_blas, mb, p.D.M, p.dh, p.din, p.ctot_b, rbb))) return rc;
-    reduce_slots_kernel<<<ceil_div(p.D.M * p.ctot_f, 256), 256, 0, st>>>(rbf, p.nb_f, p.D.M * p.ctot_f, rdf);
-    reduce_slots_kernel<<<ceil_div(p.D.M * p.ctot_b, 256), 256, 0, st>>>(rbb, p.nb_b, p.D.M * p.ctot_b, rdb);
+    {
+      ScopedTiming tm(5, st);
+      CBF_CUDA(tc_outer(mb, p.D.M, p.dh, p.din, rpart, rdb, st));
+    }
     finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dx, p.ctot_f, rdf, ws.acc_f + p.Lf.scal_off(), to_dev(gp_f),
                                                grad_flat + gl.f_P, grad_flat + gl.f_alpha, grad_flat + gl.f_S,
                                                grad_flat + gl.f_Z, grad_flat + gl.f_ell, grad_flat + gl.f_sig2);
@@ -798,7 +764,7 @@ CBF_API int cbf_timing_enable(int enable) {
 
 CBF_API int cbf_timing_read(double *ms_sum_host, int64_t *count_host) {
   if (!ms_sum_host || !count_host) { set_error("cbf_timing_read: NULL argument"); return CBF_ERR_NULL; }
-  for (int k = 0; k < 4; ++k) { ms_sum_host[k] = 0.0; count_host[k] = 0; }
+  for (int k = 0; k < 8; ++k) { ms_sum_host[k] = 0.0; count_host[k] = 0; }
   TimingPool &t = g_timing;
   for (size_t i = 0; i < t.used; ++i) {
     CBF_CUDA(cudaEventSynchronize(t.ev[2 * i + 1]));

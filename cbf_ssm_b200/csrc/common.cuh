@@ -33,11 +33,17 @@ struct GpDev {
   const float *Z, *ell, *sig2, *P, *alpha, *S;
 };
 
-// Workspace views of the outer-product operand matrices one tensor-path reverse kernel writes
-// (float32, row-major [rows][L], L = live steps x particles): k', a_bar, a^2, w, g_mean, g_var, [x~,1].
+// Outer-product operands one tensor-path reverse kernel writes for one GP (float32), in a
+// tile-major layout: the L = (live steps x particles) columns are cut into blocks of 16; block b holds
+// all R rows' 16-column segments contiguously, element (row, col) at  blk[(col/16)*R*16 + row*16 + col%16].
+// Rows: a_bar (M) | k' (M) | a^2 (M) | w (M) | g_mean (Dout) | g_var (Dout) | [x~, 1] (Din+1).
+// A warp's store of one row touches two full 64-byte segments, and the accumulation kernel reads one
+// block as a single contiguous ~26 KB stream.
 struct TcMats {
-  float *K, *Ab, *A2, *W, *Gm, *Gv, *X1;
-  size_t L;
+  float *blk;
+  size_t L;        // valid columns
+  int R;           // rows per block
+  int rAb, rK, rA2, rW, rGm, rGv, rX1;
 };
 
 // Device views into the caller's workspace.

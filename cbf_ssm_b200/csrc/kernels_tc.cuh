@@ -19,8 +19,8 @@
 // a = P k and the second contraction P b on the tensor core (b is scaled per particle by a power
 // of two into fp16 range and split the same way), the step adjoint and the k_bar / x_bar chain in
 // SIMT, and writes the operands of the parameter-adjoint outer products (a_bar, k, a^2, w, g_mean,
-// g_var, x~) as float32 rows [m][step*particle] to the workspace; the accumulation over (particle,
-// step) is then a plain GEMM (cuBLAS SGEMM in column chunks, float64 across chunks; api.cu).
+// g_var, x~) as float32 rows of a tile-major matrix (common.cuh TcMats) to the workspace; the accumulation
+// over (particle, step) is the tcgen05 split-K reduction of kernels_outer.cuh.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -603,10 +603,11 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
 }
 
 __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
+  float *b = m.blk + (col >> 4) * ((size_t)m.R * 16) + (col & 15);
   TcOut o;
-  o.K = m.K + col; o.Ab = m.Ab + col; o.A2 = m.A2 + col; o.W = m.W + col;
-  o.Gm = m.Gm + col; o.Gv = m.Gv + col; o.X1 = m.X1 + col;
-  o.ld = m.L;
+  o.Ab = b + m.rAb * 16; o.K = b + m.rK * 16; o.A2 = b + m.rA2 * 16; o.W = b + m.rW * 16;
+  o.Gm = b + m.rGm * 16; o.Gv = b + m.rGv * 16; o.X1 = b + m.rX1 * 16;
+  o.ld = 16;
   return o;
 }
 

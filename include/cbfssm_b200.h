@@ -69,6 +69,7 @@ typedef struct cbf_shape {
 #define CBF_FLAG_FORCE_REGISTER 4
 #define CBF_FLAG_FORCE_TENSOR_CORES 8
 
+
 /* Kernel-level operands of one sparse GP (gp_tf.py:103-130), float32, produced by
  * cbf_gp_prologue (or by the caller).  Dout = dx for gp_f, dx-dy for gp_b. */
 typedef struct cbf_gp {
@@ -176,12 +177,13 @@ CBF_API int cbf_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t strea
 
 /* Measurement aid for bench.py (the only thread-local state the library keeps, off by
  * default): when enabled, the four rollout kernels (0 backward-message forward,
- * 1 forward rollout, 2 forward-rollout reverse, 3 backward-message reverse) are
- * bracketed by CUDA events on the caller's stream.  cbf_timing_read synchronises on
+ * 1 forward rollout, 2 forward-rollout reverse, 3 backward-message reverse, and on the tensor
+ * path 4 / 5 the outer-product accumulation of the forward / message GP) are bracketed by CUDA
+ * events on the caller's stream.  cbf_timing_read synchronises on
  * those events and returns the summed milliseconds and launch counts per kernel since
  * the last read. */
 CBF_API int cbf_timing_enable(int enable);
-CBF_API int cbf_timing_read(double *ms_sum_host /*[4]*/, int64_t *count_host /*[4]*/);
+CBF_API int cbf_timing_read(double *ms_sum_host /*[8]*/, int64_t *count_host /*[8]*/);
 
 #ifdef __cplusplus
 }
