@@ -34,11 +34,13 @@ struct GpDev {
 };
 
 // Outer-product operands one tensor-path reverse kernel writes for one GP (float32), in a
-// tile-major layout: the L = (live steps x particles) columns are cut into blocks of 16; block b holds
-// all R rows' 16-column segments contiguously, element (row, col) at  blk[(col/16)*R*16 + row*16 + col%16].
+// tile-major layout: the L = (live steps x particles) columns are cut into blocks of 16 and each block
+// into four 4-column chunks; a block holds, chunk by chunk, all R rows' 16-byte segments contiguously:
+// element (row, col) at  blk[(col/16)*R*16 + ((col%16)/4)*R*4 + row*4 + col%4].
 // Rows: a_bar (M) | k' (M) | a^2 (M) | w (M) | g_mean (Dout) | g_var (Dout) | [x~, 1] (Din+1).
-// A warp's store of one row touches two full 64-byte segments, and the accumulation kernel reads one
-// block as a single contiguous ~26 KB stream.
+// The accumulation kernel reads one block as a single contiguous ~26 KB stream whose float4 index is
+// (chunk, row) -- exactly the order of the UMMA K-major core-matrix layout it stages it into, so both
+// its global loads and its shared stores are conflict-free and coalesced.
 struct TcMats {
   float *blk;
   size_t L;        // valid columns

@@ -603,11 +603,12 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
 }
 
 __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
-  float *b = m.blk + (col >> 4) * ((size_t)m.R * 16) + (col & 15);
+  const unsigned c = (unsigned)(col & 15);
+  float *b = m.blk + (col >> 4) * ((size_t)m.R * 16) + (size_t)(c >> 2) * ((size_t)m.R * 4) + (c & 3);
   TcOut o;
-  o.Ab = b + m.rAb * 16; o.K = b + m.rK * 16; o.A2 = b + m.rA2 * 16; o.W = b + m.rW * 16;
-  o.Gm = b + m.rGm * 16; o.Gv = b + m.rGv * 16; o.X1 = b + m.rX1 * 16;
-  o.ld = 16;
+  o.Ab = b + m.rAb * 4; o.K = b + m.rK * 4; o.A2 = b + m.rA2 * 4; o.W = b + m.rW * 4;
+  o.Gm = b + m.rGm * 4; o.Gv = b + m.rGv * 4; o.X1 = b + m.rX1 * 4;
+  o.ld = 4;
   return o;
 }
 
