@@ -95,8 +95,9 @@ __device__ __forceinline__ void split_h(float x, __half &h1, __half &h2) {
 }
 
 // Shared-memory state of one CTA: operands, resident small GP tables, barrier, TMEM base.
-template <int DIN, int DOUT, bool REV = false>
+template <int DIN, int DOUT, bool REV = false, int MC_ = 0>
 struct TcCtx {
+  static constexpr int MC = MC_;     // compile-time M (0: runtime) -- lets the M loops unroll and drop their guards
   static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   static constexpr uint32_t TMEM_COLS = REV ? 256u : 128u;
   __half *P1, *P2, *K1, *K2, *B1, *B2;
@@ -265,7 +266,8 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
                                               float (&fm)[DOUT], float (&fv)[DOUT], float *__restrict__ kout,
                                               size_t ldk, float &amax, float &kscale) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
-  const int t = threadIdx.x, M = c.M, MP = c.MP;
+  constexpr int MC = Ctx::MC;
+  const int t = threadIdx.x, M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
   {
     float il[DINP];
     ld_row<DINP>(c.il, il);
@@ -280,6 +282,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   // distances (float32) in the thread's own K1/K2 slots and finds their minimum, pass 2 forms
   // k'' = exp(-(d^2 - d^2_min)/2) in (0,1] (max exactly 1), splits and overwrites.  k' = kscale * k''.
   float d2min = 3.0e38f;
+#pragma unroll(MC ? 2 : 1)
   for (int ch = 0; ch < MP / 8; ++ch) {
     float dv[8];
 #pragma unroll
@@ -301,6 +304,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
     *reinterpret_cast<float4 *>(c.K2 + off) = make_float4(dv[4], dv[5], dv[6], dv[7]);
   }
   kscale = fast_exp2(kNegHalfLog2e * d2min);
+#pragma unroll(MC ? 2 : 1)
   for (int ch = 0; ch < MP / 8; ++ch) {
     const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
     const float4 da = *reinterpret_cast<const float4 *>(c.K1 + off), db = *reinterpret_cast<const float4 *>(c.K2 + off);
@@ -330,6 +334,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
+#pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16], kp[16];
     tmem_ld16(trow + cc * 16, a);
@@ -373,7 +378,8 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
                                               const TcOut &o, float (&xinb)[NEED], float (&Lacc)[DIN], float &sw,
                                               float &sG) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
-  const int t = threadIdx.x, M = c.M, MP = c.MP;
+  constexpr int MC = Ctx::MC;
+  const int t = threadIdx.x, M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
   const float ps = c.pscale, sig2 = c.sig2;
   const float ascale = ps * sig2 * kscale;      // a = ascale * a'' (a'' = P' k'' is what D1 holds)
   float Gs = 0.f, cbound = 0.f;
@@ -393,6 +399,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     o.X1[(size_t)DIN * o.ld] = 1.f;
   }
   // ---- b'' = a' (S gv) 2^-e -> fp16 split rows of B ----
+#pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16];
     tmem_ld16(trow1 + cc * 16, a);
@@ -426,6 +433,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   const float bs = ascale * binv;               // b_m = bs * b''_m
 #pragma unroll
   for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
+#pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float pb[16], a[16], kp[16], bb[16];
     tmem_ld16(trow2 + cc * 16, pb);
@@ -471,7 +479,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 }
 
 // =====================================================================================
-template <int DX, int DU, int DY>
+template <int DX, int DU, int DY, int MC>
 __global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, Chain
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float scratch[8];
   __shared__ float vx[16];
-  TcCtx<DIN, DH> c;
+  TcCtx<DIN, DH, false, MC> c;
   c.init(smem_raw, gp, D.M, scratch);
   if (threadIdx.x < DX) vx[threadIdx.x] = vxg[threadIdx.x];
   __syncthreads();
@@ -514,7 +522,7 @@ __global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, Chain
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
     float xt[TcCtx<DIN, DH>::DINP], amax, kscale;
-    gp_forward_tc<TcCtx<DIN, DH>, DIN, DH>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
+    gp_forward_tc<TcCtx<DIN, DH, false, MC>, DIN, DH>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
     const bool write = writer_run(t, D.R) == ch.run;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, Chain
   cta_sum_store<1>(v, scratch, part_out + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
 }
 
-template <int DX, int DU, int DY>
+template <int DX, int DU, int DY, int MC>
 __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float scratch[4 * (DY + 1)];
   __shared__ float vx[16], vy[16];
-  TcCtx<DIN, DX> c;
+  TcCtx<DIN, DX, false, MC> c;
   c.init(smem_raw, gp, D.M, scratch);
   if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
   __syncthreads();
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
     load_ytil(t + 1, yt);
     const float e = eps_f[(size_t)t * D.n_local + nr];
     float xt[TcCtx<DIN, DX>::DINP], amax, kscale;
-    gp_forward_tc<TcCtx<DIN, DX>, DIN, DX>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
+    gp_forward_tc<TcCtx<DIN, DX, false, MC>, DIN, DX>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
     const bool do_cond = D.condition || (t < D.R - 1);
     fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, xn, kl);
 #pragma unroll
@@ -616,7 +624,7 @@ __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
 // Reverse of the forward rollout on tcgen05: one CTA = 128 particles, T-1 steps.
 // Per-CTA output: scalar sums [L_j | sum w | sum G | var_x_bar | var_y_bar] at spart[cta].
 // =====================================================================================
-template <int DX, int DU, int DY>
+template <int DX, int DU, int DY, int MC>
 __global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
@@ -625,7 +633,7 @@ __global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev
                                                                    float w_kl, Workspace ws, TcMats mats,
                                                                    float *__restrict__ spart, int nsc) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using Ctx = TcCtx<DIN, DX, true>;
+  using Ctx = TcCtx<DIN, DX, true, MC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float scratch[4 * (DIN + 2 + 2 * DX)];
   __shared__ float vx[16], vy[16];
@@ -708,7 +716,7 @@ __global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev
   cta_sum_store<DIN + 2 + 2 * DX>(sc, scratch, spart + (size_t)blockIdx.x * nsc);
 }
 
-template <int DX, int DU, int DY>
+template <int DX, int DU, int DY, int MC>
 __global__ void __launch_bounds__(kTcThreads) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
@@ -718,7 +726,7 @@ __global__ void __launch_bounds__(kTcThreads) bm_reverse_tc_kernel(Dims D, Chain
                                                                    Workspace ws, TcMats mats,
                                                                    float *__restrict__ spart, int nsc) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using Ctx = TcCtx<DIN, DH, true>;
+  using Ctx = TcCtx<DIN, DH, true, MC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float scratch[4 * (DIN + 2 + 2 * DX)];
   __shared__ float vx[16];
@@ -800,6 +808,8 @@ __global__ void __launch_bounds__(kTcThreads) bm_reverse_tc_kernel(Dims D, Chain
 template <int DX, int DU, int DY>
 struct LaunchTc {
   static constexpr int DH = DX - DY, DIN = DX + DU;
+  // dims with a compile-time M = 100 instantiation (run/template.py, SpringNonlinear, Sarcos shapes)
+  static constexpr bool kHas100 = (DX == 4 && (DU == 1 || DU == 2)) || DX == 14;
   static size_t smem_b(int M) { return TcCtx<DIN, DH>::bytes(M); }
   static size_t smem_f(int M) { return TcCtx<DIN, DX>::bytes(M); }
   static size_t smem_rb(int M) { return TcCtx<DIN, DH, true>::bytes(M); }
@@ -809,23 +819,30 @@ struct LaunchTc {
                                 const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
                                 TcMats mats, float *spart, int nsc, cudaStream_t st) {
     const size_t smem = smem_rf(D.M);
-    cudaError_t e = cudaFuncSetAttribute(fw_reverse_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fw_reverse_tc_kernel<DX, DU, DY><<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(
-        D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, spart, nsc);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kernel<<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats,
+                                                                        spart, nsc);
+      return cudaGetLastError();
+    };
+    if constexpr (kHas100) { if (D.M == 100) return go(fw_reverse_tc_kernel<DX, DU, DY, 100>); }
+    return go(fw_reverse_tc_kernel<DX, DU, DY, 0>);
   }
   static cudaError_t bm_reverse(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
                                 const float *y, const float *eps_b, const float *z_b, float w_en, Workspace ws,
                                 TcMats mats, float *spart, int nsc, cudaStream_t st) {
     if (ct.count == 0) return cudaSuccess;
     const size_t smem = smem_rb(D.M);
-    cudaError_t e = cudaFuncSetAttribute(bm_reverse_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     dim3 grid(ceil_div(D.n_local, kTcThreads), ct.count);
-    bm_reverse_tc_kernel<DX, DU, DY><<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats,
-                                                                    spart, nsc);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kernel<<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats, spart, nsc);
+      return cudaGetLastError();
+    };
+    if constexpr (kHas100) { if (D.M == 100) return go(bm_reverse_tc_kernel<DX, DU, DY, 100>); }
+    return go(bm_reverse_tc_kernel<DX, DU, DY, 0>);
   }
 
   static cudaError_t bm_forward(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
@@ -833,21 +850,28 @@ struct LaunchTc {
                                 float *part_out, cudaStream_t st) {
     if (ct.count == 0) return cudaSuccess;
     const size_t smem = smem_b(D.M);
-    cudaError_t e = cudaFuncSetAttribute(bm_forward_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     dim3 grid(ceil_div(D.n_local, kTcThreads), ct.count);
-    bm_forward_tc_kernel<DX, DU, DY><<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kernel<<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
+      return cudaGetLastError();
+    };
+    if constexpr (kHas100) { if (D.M == 100) return go(bm_forward_tc_kernel<DX, DU, DY, 100>); }
+    return go(bm_forward_tc_kernel<DX, DU, DY, 0>);
   }
   static cudaError_t fw_forward(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
                                 const float *y, const float *eps_f, Workspace ws, float *part_out,
                                 cudaStream_t st) {
     const size_t smem = smem_f(D.M);
-    cudaError_t e = cudaFuncSetAttribute(fw_forward_tc_kernel<DX, DU, DY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fw_forward_tc_kernel<DX, DU, DY><<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(D, gp, vx, vy, u, y,
-                                                                                             eps_f, ws, part_out);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kernel<<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, ws, part_out);
+      return cudaGetLastError();
+    };
+    if constexpr (kHas100) { if (D.M == 100) return go(fw_forward_tc_kernel<DX, DU, DY, 100>); }
+    return go(fw_forward_tc_kernel<DX, DU, DY, 0>);
   }
 };
 
