@@ -72,7 +72,7 @@ struct ScopedTiming {
 constexpr int kMaxGridRev = 148 * 8;   // upper bound on persistent reverse CTAs (workspace sizing)
 constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kMinParticlesRegisterPath = 4096;   // one-thread-per-particle kernels below this are latency-bound
-constexpr int kMinParticlesTensorPath = 12288;    // 128-particle tcgen05 tiles need ~100 CTAs to pay off
+constexpr int kMinParticlesTensorPath = 4096;     // 128-particle tcgen05 tiles: faster from ~32 CTAs (tools/bench_cross.sh)
 
 // Live chain segments of both backward-message runs (cbfssm.py:123-136, SURVEY 8a note 5).
 static std::vector<Chain> build_chains(int T, int R) {

@@ -61,10 +61,18 @@ class BaseDS:
         if verbose:
             self.print_stats()
 
+    def stats(self):
+        """Sizes of the raw series and of the windowed sets."""
+        def samples(a):
+            return int(a.shape[0] * a.shape[1]) if a.ndim >= 2 else 0
+        return {"sequence_length": self.seq_len,
+                "train": {"samples": samples(self.train_in), "sequences": int(self.train_in_batch.shape[0])},
+                "test": {"samples": samples(self.test_in), "sequences": int(self.test_in_batch.shape[0])}}
+
     def print_stats(self):
+        st = self.stats()
         print('Dataset Stats:')
-        print('  sequence length: %d' % self.seq_len)
-        print('  train samples: %d' % (self.train_in.shape[0] * self.train_in.shape[1]))
-        print('  train sequences: %d' % self.train_in_batch.shape[0])
-        print('  test samples: %d' % (self.test_in.shape[0] * self.test_in.shape[1]))
-        print('  test sequences: %d' % self.test_in_batch.shape[0])
+        print('  sequence length: %d' % st["sequence_length"])
+        for part in ("train", "test"):
+            print('  %s samples: %d' % (part, st[part]["samples"]))
+            print('  %s sequences: %d' % (part, st[part]["sequences"]))

@@ -1,58 +1,89 @@
-"""``Trainer`` with the reference's interface and epoch semantics
-(cbfssm/training/trainer.py:10-63): per epoch one pass over the training windows with
-the ``train`` op, one pass over the test windows fetching ``loss`` only, both with
-``condition=True``; epoch loss = mean of the per-minibatch losses; ``best.ckpt`` on the
-lowest training loss, ``model.ckpt`` at the end, ``retrain`` restores ``model.ckpt``."""
+"""Epoch driver with the reference ``Trainer`` interface.
+
+Behaviour kept from cbfssm/training/trainer.py:10-63 (it is the caller of the hot path):
+
+* ``Trainer(model, model_dir).train(ds, epochs, retrain=False)``;
+* ``retrain`` restores ``<model_dir>/model.ckpt`` (run_robomove.py:47 curriculum), otherwise the
+  model is re-initialised;
+* one epoch = a pass over ``ds.train_*_batch`` fetching ``(train, loss)`` and a pass over
+  ``ds.test_*_batch`` fetching ``loss`` only, both with ``condition=True``;
+* the epoch losses are the *means of the per-minibatch losses* and are appended to
+  ``train_all`` / ``test_all``;
+* ``best.ckpt`` whenever the epoch's training loss is the lowest so far, ``model.ckpt`` at the end.
+
+Added here: particle-steps/s per epoch in ``throughput_all`` (the hot path's own metric).
+"""
 import os
+import time
 
 import numpy as np
 
 from ..model.base_model import Session
 
 try:
-    from tqdm import tqdm
+    from tqdm import tqdm as _progress
 except ImportError:  # pragma: no cover
-    tqdm = lambda x: x
+    def _progress(it):
+        return it
 
 
 class Trainer:
+
+    BEST = "best.ckpt"
+    LAST = "model.ckpt"
 
     def __init__(self, model, model_dir):
         self.model = model
         self.model_dir = model_dir
         self.train_all = []
         self.test_all = []
+        self.throughput_all = []
 
+    # -- helpers -------------------------------------------------------------------------
+    def _path(self, name):
+        return os.path.join(self.model_dir, name)
+
+    def _pass(self, sess, data_in, data_out, fetches):
+        """One pass over a set of windows; returns the mean of the per-minibatch losses."""
+        model = self.model
+        model.load_ds(sess, data_in, data_out)
+        results = model.run(sess, fetches, {model.condition: True})
+        return float(np.mean(results[-1]))          # loss is the last fetch
+
+    def _particle_steps(self, windows):
+        n_seq, seq_len = windows.shape[0], windows.shape[1]
+        return n_seq * seq_len * int(self.model.config['samples'])
+
+    # -- public --------------------------------------------------------------------------
     def train(self, ds, epochs, retrain=False, verbose=True):
-        if verbose:
-            print('\nTraining...\n')
         model = self.model
         os.makedirs(self.model_dir, exist_ok=True)
-        with model.graph.as_default():
-            with Session(model) as sess:
-                if retrain:
-                    model.saver.restore(sess, self.model_dir + '/model.ckpt')
-                else:
-                    sess.run(model.init)
+        if verbose:
+            print('\nTraining...\n')
+        with model.graph.as_default(), Session(model) as sess:
+            if retrain:
+                model.saver.restore(sess, self._path(self.LAST))
+            else:
+                sess.run(model.init)
 
-                lowest_train = float('inf')
-                for epoch in (tqdm(range(epochs)) if verbose else range(epochs)):
-                    model.load_ds(sess, ds.train_in_batch, ds.train_out_batch)
-                    train_loss = model.run(sess, (model.train, model.loss), {model.condition: True})
-                    train_loss = np.mean(train_loss[1])
+            best = float('inf')
+            epoch_iter = _progress(range(epochs)) if verbose else range(epochs)
+            for epoch in epoch_iter:
+                tic = time.perf_counter()
+                train_loss = self._pass(sess, ds.train_in_batch, ds.train_out_batch, (model.train, model.loss))
+                elapsed = time.perf_counter() - tic
+                test_loss = self._pass(sess, ds.test_in_batch, ds.test_out_batch, (model.loss,))
 
-                    model.load_ds(sess, ds.test_in_batch, ds.test_out_batch)
-                    test_loss = model.run(sess, model.loss, {model.condition: True})
-                    test_loss = np.mean(test_loss)
+                self.train_all.append(train_loss)
+                self.test_all.append(test_loss)
+                self.throughput_all.append(self._particle_steps(ds.train_in_batch) / max(elapsed, 1e-9))
+                if verbose:
+                    print('[%04d]: Train %s, Test %s  (%.3g particle-steps/s)'
+                          % (epoch, train_loss, test_loss, self.throughput_all[-1]))
 
-                    if verbose:
-                        print('[{epoch:04}]: Train {train}, Test {test}'.format(
-                            epoch=epoch, train=train_loss, test=test_loss))
-                    self.train_all.append(train_loss)
-                    self.test_all.append(test_loss)
+                if train_loss < best:
+                    best = train_loss
+                    model.saver.save(sess, self._path(self.BEST))
 
-                    if train_loss < lowest_train:
-                        model.saver.save(sess, self.model_dir + '/best.ckpt')
-                        lowest_train = train_loss
-
-                model.saver.save(sess, self.model_dir + '/model.ckpt')
+            model.saver.save(sess, self._path(self.LAST))
+        return self

@@ -64,7 +64,7 @@ typedef struct cbf_shape {
 /* Do not use the tcgen05 tensor-core forward kernels (selected by default for 48 <= M <= 128). */
 #define CBF_FLAG_NO_TENSOR_CORES 2
 /* By default the register-resident kernels are used from 4096 particles per call and the
- * tensor-core forward kernels from 12288 (below that the cooperative kernels have the lower
+ * tensor-core kernels from 4096 as well (below that the cooperative kernels have the lower
  * latency per time step).  These flags select them regardless of the particle count. */
 #define CBF_FLAG_FORCE_REGISTER 4
 #define CBF_FLAG_FORCE_TENSOR_CORES 8

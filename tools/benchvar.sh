@@ -1,4 +1,4 @@
-for lib in "" cbf_ssm_b200/libcbf_v2.so; do
+for lib in "" cbf_ssm_b200/libcbf_v4.so; do
   echo "== lib=$lib"
   CBFSSM_B200_LIB=${lib:+$PWD/$lib} python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
