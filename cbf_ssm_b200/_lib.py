@@ -50,6 +50,9 @@ _SIGNATURES = {
     "cbf_elbo_forward": (C.c_int, [C.POINTER(cbf_shape), C.POINTER(cbf_gp), C.POINTER(cbf_gp)] + [_P] * 10),
     "cbf_elbo_backward": (C.c_int, [C.POINTER(cbf_shape), C.POINTER(cbf_gp), C.POINTER(cbf_gp)] + [_P] * 7
                           + [C.POINTER(C.c_double), _P, _P, _P]),
+    "cbf_elbo_forward_half": (C.c_int, [C.POINTER(cbf_shape), C.POINTER(cbf_gp)] + [_P] * 9),
+    "cbf_elbo_backward_half": (C.c_int, [C.POINTER(cbf_shape), C.POINTER(cbf_gp)] + [_P] * 6
+                               + [C.POINTER(C.c_double), _P, _P, _P, _P]),
     "cbf_export_states": (C.c_int, [C.POINTER(cbf_shape), _P, _P, _P, _P, _P]),
     "cbf_moments": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "cbf_gp_prologue_state_doubles": (C.c_int64, [C.c_int32] * 3),

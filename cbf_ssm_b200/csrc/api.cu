@@ -107,6 +107,8 @@ struct Plan {
   AccLayout Lf, Lb;
   size_t off_X, off_H, off_Yb, off_fbm, off_ffw, off_gf, off_gb, off_accf, off_accb, off_stats, off_cpack, total;
   const DimOps *ops;
+  bool half;                     // CBFSSMHALF: no backward-message GP, x_0 supplied by the caller
+  size_t off_x0b;
   // tensor-core path (48 <= M <= 128, enough particles)
   bool tc_fwd, tc_rev;
   size_t colsf, colsb;           // columns (live steps x particles) of the operand matrices
@@ -115,7 +117,7 @@ struct Plan {
   size_t off_mf, off_mb, off_spf, off_spb, off_rdf, off_rdb;
 };
 
-constexpr size_t kTcMaxMatBytes = (size_t)96 << 30;
+constexpr size_t kTcMaxMatBytes = (size_t)64 << 30;
 constexpr int kOuterMaxGrid = 148 * 2;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -151,8 +153,12 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   D.B = s->B; D.S = s->S; D.T = s->T; D.M = s->M; D.R = s->R; D.condition = s->condition ? 1 : 0;
   D.n_offset = s->n_offset; D.n_local = s->n_local; D.kap = s->k_factor;
   D.npad = round_up(s->n_local, 32);
+  p.half = (s->flags & CBF_FLAG_HALF_MODEL) != 0;
+  D.half = p.half ? 1 : 0;
+  D.ncond = p.half ? s->dy : s->dx;
   p.ptiles = ceil_div(s->n_local, kNP);            // upper bound for every path (smallest CTA tile)
   p.chains = build_chains(s->T, s->R);
+  if (p.half) p.chains.clear();
   p.slots_per_cta = 1;
   if (p.ops) {
     p.ops->layouts(s->M, &p.Lf, &p.Lb);
@@ -175,6 +181,7 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   p.off_accb = o; o = align_up(o + sizeof(double) * p.Lb.slot(), 256);
   p.off_stats = o; o = align_up(o + sizeof(double) * (p.dy + 2), 256);
   p.off_cpack = o; o = align_up(o + sizeof(float) * 2 * 2048, 256);
+  p.off_x0b = o; o = align_up(o + sizeof(float) * p.dx * np, 256);
   // ---- tensor-core path ----
   p.tc_fwd = p.tc_rev = false;
   if (p.ops && p.ops->fw_forward_tc != nullptr && s->M >= 48 && s->M <= 128 &&
@@ -191,7 +198,7 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
     const size_t blkf = (p.colsf + 15) / 16, blkb = (p.colsb + 15) / 16;
     const size_t bytes = sizeof(float) * 16 * (rows_f * blkf + rows_b * blkb);
     p.tc_rev = p.tc_fwd && p.ops->fw_reverse_tc != nullptr && p.ops->smem_tc(s->M, 2) <= kMaxSmem &&
-               p.ops->smem_tc(s->M, 3) <= kMaxSmem && bytes <= kTcMaxMatBytes && p.colsf > 0 && p.colsb > 0 &&
+               p.ops->smem_tc(s->M, 3) <= kMaxSmem && bytes <= kTcMaxMatBytes && p.colsf > 0 && (p.colsb > 0 || p.half) &&
                p.colsf < ((size_t)1 << 31) && p.colsb < ((size_t)1 << 31);
     if (p.tc_rev) {
       p.nsc_f = p.Lf.slot() - p.Lf.scal_off();
@@ -254,6 +261,8 @@ static Workspace bind_workspace(const Plan &p, void *base) {
   w.acc_b = reinterpret_cast<double *>(b + p.off_accb);
   w.stats = reinterpret_cast<double *>(b + p.off_stats);
   w.cpack = reinterpret_cast<float *>(b + p.off_cpack);
+  w.x0 = nullptr;
+  w.x0b = reinterpret_cast<float *>(b + p.off_x0b);
   w.npad = p.D.npad;
   return w;
 }
@@ -377,6 +386,17 @@ __global__ void finalize_tc_grad_kernel(int M, int Din, int Dout, int Ctot, cons
   }
   for (int j = tid; j < Din; j += nt) gell[j] = sc[j] / (double)gp.ell[j];
   if (tid == 0) gsig2[0] = sc[Din] / sig2 + sc[Din + 1];
+}
+
+// CBFSSMHALF: d loss / d x_0[b][j] = sum over the S particles of sequence b (x_0 is tiled, cbfssmhalf.py:80,92)
+__global__ void reduce_x0b_kernel(const float *__restrict__ x0b, int npad, int S, int nb, int dx,
+                                  double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb * dx) return;
+  const int b = i / dx, j = i % dx;
+  double s = 0.0;
+  for (int k = 0; k < S; ++k) s += (double)x0b[(size_t)j * npad + (size_t)b * S + k];
+  out[i] = s;
 }
 
 __global__ void finalize_noise_grad_kernel(int dx, int dy, int Din, const double *__restrict__ sc_f,
@@ -572,20 +592,25 @@ CBF_API int cbf_grad_layout_get(const cbf_shape *shape, cbf_grad_layout *out) {
   return 0;
 }
 
-CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
-                     const float *var_y, const float *u, const float *y, const float *eps_b, const float *z_b,
-                     const float *eps_f, double *terms, void *workspace, void *stream) {
+}  // extern "C"
+
+static int elbo_forward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
+                             const float *var_y, const float *u, const float *y, const float *x0,
+                             const float *eps_b, const float *z_b, const float *eps_f, double *terms,
+                             void *workspace, void *stream) {
   Plan p;
   int rc = make_plan(shape, p, true);
   if (rc) return rc;
-  if ((rc = check_gp(gp_f, "gp_f")) || (rc = check_gp(gp_b, "gp_b"))) return rc;
-  if (!var_x || !var_y || !u || !y || !eps_b || !z_b || (!eps_f && shape->T > 1) || !terms || !workspace) {
+  if ((rc = check_gp(gp_f, "gp_f")) || (!p.half && (rc = check_gp(gp_b, "gp_b")))) return rc;
+  if (!var_x || !var_y || !u || !y || (!p.half && (!eps_b || !z_b)) || (p.half && !x0) ||
+      (!eps_f && shape->T > 1) || !terms || !workspace) {
     set_error("cbf_elbo_forward: NULL argument");
     return CBF_ERR_NULL;
   }
   if (misaligned(workspace)) { set_error("workspace must be 16-byte aligned"); return CBF_ERR_ALIGNMENT; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace ws = bind_workspace(p, workspace);
+  ws.x0 = x0;
   const int nch = (int)p.chains.size();
   // tensor-core forward kernels: a 128-particle tile makes the M x M contraction a real GEMM
   const bool tc = p.tc_fwd;
@@ -609,21 +634,45 @@ CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const c
   return 0;
 }
 
-CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
-                      const float *var_y, const float *u, const float *y, const float *eps_b, const float *z_b,
-                      const float *eps_f, const double *term_weights_host, double *grad_flat, void *workspace,
-                      void *stream) {
+extern "C" {
+
+CBF_API int cbf_elbo_forward(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
+                     const float *var_y, const float *u, const float *y, const float *eps_b, const float *z_b,
+                     const float *eps_f, double *terms, void *workspace, void *stream) {
+  if (shape && (shape->flags & CBF_FLAG_HALF_MODEL)) { set_error("use cbf_elbo_forward_half with CBF_FLAG_HALF_MODEL"); return CBF_ERR_INVALID_SHAPE; }
+  return elbo_forward_impl(shape, gp_f, gp_b, var_x, var_y, u, y, nullptr, eps_b, z_b, eps_f, terms, workspace, stream);
+}
+
+CBF_API int cbf_elbo_forward_half(const cbf_shape *shape, const cbf_gp *gp_f, const float *var_x, const float *var_y,
+                          const float *u, const float *y, const float *x0, const float *eps_f, double *terms,
+                          void *workspace, void *stream) {
+  if (!shape || !(shape->flags & CBF_FLAG_HALF_MODEL)) { set_error("cbf_elbo_forward_half needs CBF_FLAG_HALF_MODEL in shape.flags"); return CBF_ERR_INVALID_SHAPE; }
+  return elbo_forward_impl(shape, gp_f, nullptr, var_x, var_y, u, y, x0, nullptr, nullptr, eps_f, terms, workspace, stream);
+}
+
+}  // extern "C"
+
+static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
+                              const float *var_y, const float *u, const float *y, const float *x0,
+                              const float *eps_b, const float *z_b, const float *eps_f,
+                              const double *term_weights_host, double *grad_flat, double *x0_bar, void *workspace,
+                              void *stream) {
   Plan p;
   int rc = make_plan(shape, p, true);
   if (rc) return rc;
-  if ((rc = check_gp(gp_f, "gp_f")) || (rc = check_gp(gp_b, "gp_b"))) return rc;
-  if (!var_x || !var_y || !u || !y || !eps_b || !z_b || (!eps_f && shape->T > 1) || !term_weights_host ||
-      !grad_flat || !workspace) {
+  if ((rc = check_gp(gp_f, "gp_f")) || (!p.half && (rc = check_gp(gp_b, "gp_b")))) return rc;
+  if (!var_x || !var_y || !u || !y || (!p.half && (!eps_b || !z_b)) || (p.half && (!x0 || !x0_bar)) ||
+      (!eps_f && shape->T > 1) || !term_weights_host || !grad_flat || !workspace) {
     set_error("cbf_elbo_backward: NULL argument");
     return CBF_ERR_NULL;
   }
+  if (p.half && (shape->n_local % shape->S != 0 || shape->n_offset % shape->S != 0)) {
+    set_error("CBFSSMHALF needs a sequence-aligned shard (n_offset, n_local multiples of S)");
+    return CBF_ERR_INVALID_SHAPE;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace ws = bind_workspace(p, workspace);
+  ws.x0 = x0;
   const cbf_grad_layout gl = grad_layout(p);
   const float w_ll = (float)term_weights_host[0], w_kl = (float)term_weights_host[1],
               w_en = (float)term_weights_host[2];
@@ -657,16 +706,17 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
       ScopedTiming tm(4, st);
       CBF_CUDA(tc_outer(mf, p.D.M, p.dx, p.din, rpart, rdf, st));
     }
-    {
+    if (!p.half) {
       ScopedTiming tm(5, st);
       CBF_CUDA(tc_outer(mb, p.D.M, p.dh, p.din, rpart, rdb, st));
     }
     finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dx, p.ctot_f, rdf, ws.acc_f + p.Lf.scal_off(), to_dev(gp_f),
                                                grad_flat + gl.f_P, grad_flat + gl.f_alpha, grad_flat + gl.f_S,
                                                grad_flat + gl.f_Z, grad_flat + gl.f_ell, grad_flat + gl.f_sig2);
-    finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dh, p.ctot_b, rdb, ws.acc_b + p.Lb.scal_off(), to_dev(gp_b),
-                                               grad_flat + gl.b_P, grad_flat + gl.b_alpha, grad_flat + gl.b_S,
-                                               grad_flat + gl.b_Z, grad_flat + gl.b_ell, grad_flat + gl.b_sig2);
+    if (!p.half)
+      finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dh, p.ctot_b, rdb, ws.acc_b + p.Lb.scal_off(), to_dev(gp_b),
+                                                 grad_flat + gl.b_P, grad_flat + gl.b_alpha, grad_flat + gl.b_S,
+                                                 grad_flat + gl.b_Z, grad_flat + gl.b_ell, grad_flat + gl.b_sig2);
     CBF_CUDA(cudaGetLastError());
   } else {
   // reverse of the forward rollout (writes the y2 adjoints), then of the message chains
@@ -701,15 +751,41 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
   finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lf, ws.acc_f, to_dev(gp_f), grad_flat + gl.f_P, grad_flat + gl.f_alpha,
                                              grad_flat + gl.f_S, grad_flat + gl.f_Z, grad_flat + gl.f_ell,
                                              grad_flat + gl.f_sig2);
-  finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lb, ws.acc_b, to_dev(gp_b), grad_flat + gl.b_P, grad_flat + gl.b_alpha,
-                                             grad_flat + gl.b_S, grad_flat + gl.b_Z, grad_flat + gl.b_ell,
-                                             grad_flat + gl.b_sig2);
+  if (!p.half)
+    finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lb, ws.acc_b, to_dev(gp_b), grad_flat + gl.b_P, grad_flat + gl.b_alpha,
+                                               grad_flat + gl.b_S, grad_flat + gl.b_Z, grad_flat + gl.b_ell,
+                                               grad_flat + gl.b_sig2);
+  }
+  if (p.half) {   // no backward-message GP: its block of the flat gradient is zero; x_0 adjoint per sequence
+    CBF_CUDA(cudaMemsetAsync(grad_flat + gl.b_P, 0, sizeof(double) * (size_t)(gl.var_x - gl.b_P), st));
+    const int nb = p.D.n_local / p.D.S;
+    reduce_x0b_kernel<<<ceil_div(nb * p.dx, 256), 256, 0, st>>>(ws.x0b, ws.npad, p.D.S, nb, p.dx, x0_bar);
   }
   finalize_noise_grad_kernel<<<1, 32 * ceil_div(p.dx, 32), 0, st>>>(
       p.dx, p.dy, p.din, ws.acc_f + p.Lf.scal_off(), ws.acc_b + p.Lb.scal_off(), ws.stats, var_y, (double)term_weights_host[0],
       (double)p.D.n_local * p.D.T, grad_flat + gl.var_x, grad_flat + gl.var_y);
   CBF_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" {
+
+CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const cbf_gp *gp_b, const float *var_x,
+                      const float *var_y, const float *u, const float *y, const float *eps_b, const float *z_b,
+                      const float *eps_f, const double *term_weights_host, double *grad_flat, void *workspace,
+                      void *stream) {
+  if (shape && (shape->flags & CBF_FLAG_HALF_MODEL)) { set_error("use cbf_elbo_backward_half with CBF_FLAG_HALF_MODEL"); return CBF_ERR_INVALID_SHAPE; }
+  return elbo_backward_impl(shape, gp_f, gp_b, var_x, var_y, u, y, nullptr, eps_b, z_b, eps_f, term_weights_host,
+                            grad_flat, nullptr, workspace, stream);
+}
+
+CBF_API int cbf_elbo_backward_half(const cbf_shape *shape, const cbf_gp *gp_f, const float *var_x, const float *var_y,
+                           const float *u, const float *y, const float *x0, const float *eps_f,
+                           const double *term_weights_host, double *grad_flat, double *x0_bar, void *workspace,
+                           void *stream) {
+  if (!shape || !(shape->flags & CBF_FLAG_HALF_MODEL)) { set_error("cbf_elbo_backward_half needs CBF_FLAG_HALF_MODEL in shape.flags"); return CBF_ERR_INVALID_SHAPE; }
+  return elbo_backward_impl(shape, gp_f, nullptr, var_x, var_y, u, y, x0, nullptr, nullptr, eps_f, term_weights_host,
+                            grad_flat, x0_bar, workspace, stream);
 }
 
 CBF_API int cbf_export_states(const cbf_shape *shape, const float *y, float *x_final, float *y_tilde,

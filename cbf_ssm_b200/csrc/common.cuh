@@ -61,6 +61,8 @@ struct Workspace {
   double *acc_b;   // [slot_b]
   double *stats;   // sse[dy], kl_x, entropy of this shard (float64)
   float *cpack;    // [2][2048] packed constant-bank images of the two GPs (register path)
+  const float *x0; // CBFSSMHALF: x_0 per sequence [B][dx] (output of the recognition model)
+  float *x0b;      // CBFSSMHALF: adjoint of x_0 per particle [dx][npad]
   int npad;
 };
 
@@ -68,6 +70,8 @@ struct Workspace {
 struct Dims {
   int B, S, T, M, R, condition, n_offset, n_local, npad;
   float kap;
+  int half;    // 1: CBFSSMHALF -- x_0 from ws.x0, no backward message, only the first dy dims conditioned
+  int ncond;   // conditioned state dims: dx (CBFSSM) or dy (CBFSSMHALF)
 };
 
 inline __host__ __device__ int writer_run(int t, int R) { return (t % (2 * R)) < R ? 0 : 1; }

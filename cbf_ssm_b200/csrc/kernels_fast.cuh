@@ -673,13 +673,17 @@ __global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
     for (int j = 0; j < DY; ++j) yt[j] = yb[t * DY + j];
     const float *Hp = ws.H + (((size_t)writer_run(t, D.R) * D.T + t) * DH) * np + nr;
 #pragma unroll
-    for (int j = 0; j < DH; ++j) yt[DY + j] = Hp[j * np];
+    for (int j = 0; j < DH; ++j) yt[DY + j] = D.half ? 0.f : Hp[j * np];
   };
 
   float x[DX], sse[DY + 1], kl = 0.f;
 #pragma unroll
   for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
   load_ytil(0, x);
+  if (D.half) {   // x_0 from the recognition model (cbfssmhalf.py:103)
+#pragma unroll
+    for (int j = 0; j < DX; ++j) x[j] = ws.x0[(size_t)b * DX + j];
+  }
 #pragma unroll 1
   for (int t = 0; t < D.T; ++t) {
     compiler_fence();
@@ -700,7 +704,7 @@ __global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
     const float e = eps_f[(size_t)t * D.n_local + nr];
     gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
     const bool do_cond = D.condition || (t < D.R - 1);
-    fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, xn, kl);
+    fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, xn, kl);
 #pragma unroll
     for (int j = 0; j < DX; ++j) x[j] = xn[j];
   }
@@ -774,13 +778,13 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
       {
         const float *Hp = ws.H + (((size_t)writer_run(t + 1, D.R) * D.T + (t + 1)) * DH) * np + nr;
 #pragma unroll
-        for (int j = 0; j < DH; ++j) yt[DY + j] = Hp[j * np];
+        for (int j = 0; j < DH; ++j) yt[DY + j] = D.half ? 0.f : Hp[j * np];
       }
       const float e = eps_f[(size_t)t * D.n_local + nr];
       gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
       const bool do_cond = D.condition || (t < D.R - 1);
       float fmb[DX], fvb[DX], ytb[DX];
-      fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
+      fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
       if (live) {
         float *Yp = ws.Yb + ((size_t)(t + 1) * DH) * np + nl;
 #pragma unroll
@@ -801,7 +805,10 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
         xb[j] = xinb[j] + fmb[j] + lg;
       }
     }
-    if (live) {
+    if (live && D.half) {   // CBFSSMHALF: adjoint of the recognition model's x_0 (all dims)
+#pragma unroll
+      for (int j = 0; j < DX; ++j) ws.x0b[j * np + nl] = xb[j];
+    } else if (live) {
       float *Yp = ws.Yb + nl;
 #pragma unroll
       for (int j = 0; j < DH; ++j) Yp[j * np] = xb[DY + j];

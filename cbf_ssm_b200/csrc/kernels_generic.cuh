@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) fw_forward_kernel(Dims D, GpDev gp, const
     for (int j = 0; j < DY; ++j) yt[j] = yb[t * DY + j];
     const float *Hp = ws.H + (((size_t)writer_run(t, D.R) * D.T + t) * DH) * np + nr;
 #pragma unroll
-    for (int j = 0; j < DH; ++j) yt[DY + j] = live ? Hp[j * np] : 0.f;
+    for (int j = 0; j < DH; ++j) yt[DY + j] = (live && !D.half) ? Hp[j * np] : 0.f;
   };
 
   float x[DX], sse[DY + 1];
@@ -435,6 +435,10 @@ __global__ void __launch_bounds__(256) fw_forward_kernel(Dims D, GpDev gp, const
   for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
   float kl = 0.f;
   load_ytil(0, x);                                       // x_0 = y_tilde[:, 0]  (cbfssm.py:168)
+  if (D.half) {                                          // x_0 from the recognition model (cbfssmhalf.py:103)
+#pragma unroll
+    for (int j = 0; j < DX; ++j) x[j] = ws.x0[(size_t)b * DX + j];
+  }
 #pragma unroll 1
   for (int t = 0; t < D.T; ++t) {
     if (part == 0 && live) {
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(256) fw_forward_kernel(Dims D, GpDev gp, const
     const float e = live ? eps_f[(size_t)t * D.n_local + nl] : 0.f;
     gp_forward_coop<DIN, DX, false>(g, kk, nullptr, red, part, parts, n, xin, xt, fm, fv);
     const bool do_cond = D.condition || (t < D.R - 1);   // cbfssm.py:227
-    fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, xn, kl);
+    fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, xn, kl);
 #pragma unroll
     for (int j = 0; j < DX; ++j) x[j] = xn[j];
   }
@@ -535,13 +539,13 @@ __global__ void __launch_bounds__(256) fw_reverse_kernel(Dims D, GpDev gp, const
       {
         const float *Hp = ws.H + (((size_t)writer_run(t + 1, D.R) * D.T + (t + 1)) * DH) * np + nr;
 #pragma unroll
-        for (int j = 0; j < DH; ++j) yt[DY + j] = live ? Hp[j * np] : 0.f;
+        for (int j = 0; j < DH; ++j) yt[DY + j] = (live && !D.half) ? Hp[j * np] : 0.f;
       }
       const float e = live ? eps_f[(size_t)t * D.n_local + nl] : 0.f;
       gp_forward_coop<DIN, DX, true>(g, kk, aa, red, part, parts, n, xin, xt, fm, fv);
       const bool do_cond = D.condition || (t < D.R - 1);
       float fmb[DX], fvb[DX], ytb[DX];
-      fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, accum);
+      fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, accum);
       if (!live) {   // padding particles must not feed the parameter adjoints
 #pragma unroll
         for (int j = 0; j < DX; ++j) { fmb[j] = 0.f; fvb[j] = 0.f; }
@@ -562,7 +566,10 @@ __global__ void __launch_bounds__(256) fw_reverse_kernel(Dims D, GpDev gp, const
       }
       __syncthreads();
     }
-    if (accum) {   // x_0 = y_tilde[:,0]: hidden part flows to y2[0]   (cbfssm.py:168)
+    if (accum && D.half) {   // CBFSSMHALF: adjoint of the recognition model's x_0 (all dims)
+#pragma unroll
+      for (int j = 0; j < DX; ++j) ws.x0b[j * np + nl] = xb[j];
+    } else if (accum) {      // x_0 = y_tilde[:,0]: hidden part flows to y2[0]   (cbfssm.py:168)
       float *Yp = ws.Yb + nl;
 #pragma unroll
       for (int j = 0; j < DH; ++j) Yp[j * np] = xb[DY + j];

@@ -10,13 +10,15 @@ namespace cbf {
 template <int DX>
 __device__ __forceinline__ void fw_step(const float (&x)[DX], const float (&fm0)[DX], const float (&fv0)[DX],
                                         const float (&yt)[DX], float eps, const float *__restrict__ vx,
-                                        const float *__restrict__ vyp, float kap, bool do_cond,
+                                        const float *__restrict__ vyp, float kap, bool do_cond, int ncond,
                                         float (&xn)[DX], float &kl) {
+  // ncond: leading state dims that are conditioned on y~ (dx for CBFSSM; dy for CBFSSMHALF,
+  // cbfssmhalf.py:144-149, whose remaining dims have k = 0: mu = fmean, sig = fvar, KL summand 0)
 #pragma unroll
   for (int j = 0; j < DX; ++j) {
     const float fm = fm0[j] + x[j];          // :205
     const float fv = fv0[j] + vx[j];         // :206
-    if (do_cond) {
+    if (do_cond && j < ncond) {
       const float vy = vyp[j] + (kap - 1.f) * fv;   // :214
       const float s = vy + fv;                      // :216
       const float kg = fv / s;                      // :217
@@ -38,15 +40,16 @@ template <int DX>
 __device__ __forceinline__ void fw_step_adjoint(const float (&x)[DX], const float (&fm0)[DX],
                                                 const float (&fv0)[DX], const float (&yt)[DX], float eps,
                                                 const float *__restrict__ vx, const float *__restrict__ vyp,
-                                                float kap, bool do_cond, float w_kl, const float (&xb)[DX],
-                                                float (&fmb)[DX], float (&fvb)[DX], float (&ytb)[DX],
-                                                float (&vxacc)[DX], float (&vyacc)[DX], bool accumulate) {
+                                                float kap, bool do_cond, int ncond, float w_kl,
+                                                const float (&xb)[DX], float (&fmb)[DX], float (&fvb)[DX],
+                                                float (&ytb)[DX], float (&vxacc)[DX], float (&vyacc)[DX],
+                                                bool accumulate) {
 #pragma unroll
   for (int j = 0; j < DX; ++j) {
     const float fm = fm0[j] + x[j];
     const float fv = fv0[j] + vx[j];
     float fmb_j, fvb_j;
-    if (do_cond) {
+    if (do_cond && j < ncond) {
       const float vy = vyp[j] + (kap - 1.f) * fv;
       const float s = vy + fv;
       const float rs = 1.f / s;

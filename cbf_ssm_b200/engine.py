@@ -49,6 +49,7 @@ class ModelDims:
     recog_len: int
     k_factor: float = 1.0
     loss_factors: tuple = (10.0, 0.0)
+    half: bool = False        # CBFSSMHALF (cbfssm/model/cbfssmhalf.py): no backward GP, var_y of length dim_y
 
     @property
     def dim_h(self):
@@ -63,14 +64,15 @@ def param_shapes(d: ModelDims):
     """Name -> shape of the 12 raw tensors, in the reference's creation order."""
     M, din = d.ind_pnt_num, d.dim_in
     out = {}
-    for tag, dout in (("f", d.dim_x), ("b", d.dim_h)):
+    for tag, dout in ((("f", d.dim_x),) if d.half else (("f", d.dim_x), ("b", d.dim_h))):
         out[f"{tag}.zeta_pos"] = (M, din)
         out[f"{tag}.zeta_mean"] = (M, dout)
         out[f"{tag}.zeta_var_unc"] = (M, dout)
         out[f"{tag}.variance_unc"] = ()
         out[f"{tag}.lengthscales_unc"] = (din,)
     out["var_x_unc"] = (d.dim_x,)
-    out["var_y_unc"] = (d.dim_x,)      # sic: length dim_x (cbfssm.py:53, run/template.py:37)
+    # CBFSSM: length dim_x, sic (cbfssm.py:53, run/template.py:37); CBFSSMHALF: dim_y (cbfssmhalf.py:36)
+    out["var_y_unc"] = (d.dim_y,) if d.half else (d.dim_x,)
     return out
 
 
@@ -80,14 +82,15 @@ def init_param_arrays(d: ModelDims, config: dict, seed: Optional[int] = None) ->
     rs = np.random.RandomState(seed) if seed is not None else np.random
     M, din = d.ind_pnt_num, d.dim_in
     out = {}
-    for tag, dout in (("f", d.dim_x), ("b", d.dim_h)):
+    for tag, dout in ((("f", d.dim_x),) if d.half else (("f", d.dim_x), ("b", d.dim_h))):
         out[f"{tag}.zeta_pos"] = rs.uniform(low=-config["zeta_pos"], high=config["zeta_pos"], size=(M, din))
         out[f"{tag}.zeta_mean"] = config["zeta_mean"] * rs.rand(M, dout)
         out[f"{tag}.zeta_var_unc"] = _softplus_inverse(config["zeta_var"] * np.ones((M, dout)))
         out[f"{tag}.variance_unc"] = _softplus_inverse(config["gp_var"]).reshape(())
         out[f"{tag}.lengthscales_unc"] = _softplus_inverse(np.asarray([config["gp_len"]] * din, dtype=np.float64))
     out["var_x_unc"] = _softplus_inverse(config["var_x"])
-    out["var_y_unc"] = _softplus_inverse(config["var_y"])
+    out["var_y_unc"] = _softplus_inverse(np.asarray(config["var_y"], dtype=np.float64)[:d.dim_y] if d.half
+                                         else config["var_y"])
     return out
 
 
@@ -145,10 +148,13 @@ class ElboEngine:
             self.offsets[n] = (o, sz)
             o += sz
         self.gp_f = _GpBuffers(d.ind_pnt_num, d.dim_in, d.dim_x, self.device, self.lib)
-        self.gp_b = _GpBuffers(d.ind_pnt_num, d.dim_in, d.dim_h, self.device, self.lib)
+        self.gp_b = None if d.half else _GpBuffers(d.ind_pnt_num, d.dim_in, d.dim_h, self.device, self.lib)
         self.var_x = torch.zeros(max(d.dim_x, 4), dtype=F32, device=self.device)
         self.var_y = torch.zeros(max(d.dim_x, 4), dtype=F32, device=self.device)
         self.terms = torch.zeros(4, dtype=F64, device=self.device)
+        self._scratch32 = torch.zeros(max(d.dim_x, 4), dtype=F32, device=self.device)
+        self._scratch64 = torch.zeros(max(d.dim_x, 4), dtype=F64, device=self.device)
+        self.x0_bar = None        # CBFSSMHALF: d loss / d x0 [nb, dim_x] after backward()
         self._ws = None
         self._ws_key = None
         self._gl = None
@@ -182,7 +188,8 @@ class ElboEngine:
         d = self.dims
         n_local = B * d.samples - n_offset if n_local is None else n_local
         return cbf_shape(B, d.samples, T, d.ind_pnt_num, d.dim_x, d.dim_u, d.dim_y, d.recog_len,
-                         1 if condition else 0, n_offset, n_local, float(d.k_factor), int(self.flags))
+                         1 if condition else 0, n_offset, n_local, float(d.k_factor),
+                         int(self.flags) | (32 if d.half else 0))
 
     def _ensure_workspace(self, shape):
         key = (shape.B, shape.T, shape.n_local)
@@ -201,15 +208,22 @@ class ElboEngine:
     def prologue(self):
         """Raw tensors -> float32 kernel operands, KL(q(u)||p(u)) per GP (float64)."""
         lib, st, d = self.lib, self._stream(), self.dims
-        check(lib.cbf_noise_forward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
-                                    ptr(self.var_x), ptr(self.var_y), st))
-        for tag, g in (("f", self.gp_f), ("b", self.gp_b)):
+        if d.half:      # var_x has dx entries, var_y only dy: constrain them separately
+            check(lib.cbf_noise_forward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_x_unc")),
+                                        ptr(self.var_x), ptr(self._scratch32), st))
+            check(lib.cbf_noise_forward(d.dim_y, ptr(self.view("var_y_unc")), ptr(self.view("var_y_unc")),
+                                        ptr(self.var_y), ptr(self._scratch32), st))
+            self.launches += 1
+        else:
+            check(lib.cbf_noise_forward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
+                                        ptr(self.var_x), ptr(self.var_y), st))
+        for tag, g in ((("f", self.gp_f),) if d.half else (("f", self.gp_f), ("b", self.gp_b))):
             check(lib.cbf_gp_prologue(g.M, g.din, g.dout, *(ptr(self.view(f"{tag}.{f}")) for f in GP_FIELDS),
                                       ptr(g.Z), ptr(g.ell), ptr(g.sig2), ptr(g.P), ptr(g.alpha), ptr(g.S),
                                       ptr(g.kl), ptr(g.state), st))
-        self.launches += 3
+        self.launches += 2 if d.half else 3
 
-    def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True):
+    def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True, x0=None):
         """u [B,T,du], y [B,T,dy] float32 device tensors; draws float32 device tensors
         eps_b/z_b [2,T,n_local], eps_f [T-1,n_local].  Returns a dict of 0-d device
         tensors (this shard's loglik/kl_x/entropy; loss is global when a group is set
@@ -219,12 +233,19 @@ class ElboEngine:
         self._ensure_workspace(shape)
         if run_prologue:
             self.prologue()
-        check(self.lib.cbf_elbo_forward(C.byref(shape), C.byref(self.gp_f.c), C.byref(self.gp_b.c),
-                                        ptr(self.var_x), ptr(self.var_y), ptr(u), ptr(y), ptr(eps_b), ptr(z_b),
-                                        ptr(eps_f), ptr(self.terms), ptr(self._ws), self._stream()))
+        if self.dims.half:
+            if x0 is None:
+                raise ValueError("CBFSSMHALF: forward needs x0 [B, dim_x] from the recognition model")
+            check(self.lib.cbf_elbo_forward_half(C.byref(shape), C.byref(self.gp_f.c), ptr(self.var_x), ptr(self.var_y),
+                                                 ptr(u), ptr(y), ptr(x0), ptr(eps_f), ptr(self.terms), ptr(self._ws),
+                                                 self._stream()))
+        else:
+            check(self.lib.cbf_elbo_forward(C.byref(shape), C.byref(self.gp_f.c), C.byref(self.gp_b.c),
+                                            ptr(self.var_x), ptr(self.var_y), ptr(u), ptr(y), ptr(eps_b), ptr(z_b),
+                                            ptr(eps_f), ptr(self.terms), ptr(self._ws), self._stream()))
         self._shape = shape
-        self._saved = (u, y, eps_b, z_b, eps_f)
-        self._nb = count_chain_batches(T, self.dims.recog_len)
+        self._saved = (u, y, eps_b, z_b, eps_f, x0)
+        self._nb = 0 if self.dims.half else count_chain_batches(T, self.dims.recog_len)
         # register path: one operand-pack kernel in front of each rollout kernel
         self._packs = 1 if (self.kernel_path == 2 and not (self.flags & 1)) else 0
         self.launches += self._nb * (1 + self._packs) + 1 + self._packs + 1
@@ -234,7 +255,11 @@ class ElboEngine:
         d = self.dims
         l1, l2 = (float(v) for v in d.loss_factors)
         S = float(d.samples)
-        kl_f, kl_b = self.gp_f.kl[0], self.gp_b.kl[0]
+        kl_f = self.gp_f.kl[0]
+        if d.half:      # cbfssmhalf.py:188-191: no entropy term, one inducing KL
+            elbo = (l1 / S) * (terms[0] - terms[1]) - kl_f
+            return dict(loss=-elbo, loglik=terms[0], kl_x=terms[1], entropy=terms[2], kl_z_f=kl_f)
+        kl_b = self.gp_b.kl[0]
         elbo = (l1 / S) * (terms[0] - terms[1]) + (l2 / S) * terms[2] - kl_f - kl_b    # cbfssm.py:257-261
         return dict(loss=-elbo, loglik=terms[0], kl_x=terms[1], entropy=terms[2], kl_z_f=kl_f, kl_z_b=kl_b)
 
@@ -243,27 +268,44 @@ class ElboEngine:
         With a process group: all-reduces [kernel-level gradient | ELBO terms] once, so
         every rank ends with the global gradient and ``self.terms`` holds global terms."""
         lib, st, d, shape, gl = self.lib, self._stream(), self.dims, self._shape, self._gl
-        u, y, eps_b, z_b, eps_f = self._saved
+        u, y, eps_b, z_b, eps_f, x0 = self._saved
         l1, l2 = (float(v) for v in d.loss_factors)
         S = float(d.samples)
         w = (C.c_double * 3)(-l1 / S, l1 / S, -l2 / S)
         gflat = self._gflat
-        check(lib.cbf_elbo_backward(C.byref(shape), C.byref(self.gp_f.c), C.byref(self.gp_b.c), ptr(self.var_x),
-                                    ptr(self.var_y), ptr(u), ptr(y), ptr(eps_b), ptr(z_b), ptr(eps_f), w,
-                                    ptr(gflat), ptr(self._ws), st))
+        if d.half:
+            nb = shape.n_local // d.samples
+            if self.x0_bar is None or self.x0_bar.shape[0] != nb:
+                self.x0_bar = torch.zeros(nb, d.dim_x, dtype=F64, device=self.device)
+            check(lib.cbf_elbo_backward_half(C.byref(shape), C.byref(self.gp_f.c), ptr(self.var_x), ptr(self.var_y),
+                                             ptr(u), ptr(y), ptr(x0), ptr(eps_f), w, ptr(gflat), ptr(self.x0_bar),
+                                             ptr(self._ws), st))
+        else:
+            check(lib.cbf_elbo_backward(C.byref(shape), C.byref(self.gp_f.c), C.byref(self.gp_b.c), ptr(self.var_x),
+                                        ptr(self.var_y), ptr(u), ptr(y), ptr(eps_b), ptr(z_b), ptr(eps_f), w,
+                                        ptr(gflat), ptr(self._ws), st))
         if self.group is not None:
             gflat[gl.total:gl.total + 3].copy_(self.terms[:3])
             torch.distributed.all_reduce(gflat, group=self.group)
             self.terms[:3].copy_(gflat[gl.total:gl.total + 3])
         at = lambda off: C.c_void_p(gflat.data_ptr() + 8 * off)
         gat = lambda name: ptr(self.view(name, self.grad))
-        for tag, g, o in (("f", self.gp_f, (gl.f_P, gl.f_alpha, gl.f_S, gl.f_Z, gl.f_ell, gl.f_sig2)),
-                          ("b", self.gp_b, (gl.b_P, gl.b_alpha, gl.b_S, gl.b_Z, gl.b_ell, gl.b_sig2))):
+        gps = [("f", self.gp_f, (gl.f_P, gl.f_alpha, gl.f_S, gl.f_Z, gl.f_ell, gl.f_sig2))]
+        if not d.half:
+            gps.append(("b", self.gp_b, (gl.b_P, gl.b_alpha, gl.b_S, gl.b_Z, gl.b_ell, gl.b_sig2)))
+        for tag, g, o in gps:
             check(lib.cbf_gp_prologue_backward(g.M, g.din, g.dout, *(at(x) for x in o), 1.0, ptr(g.state),
                                                *(gat(f"{tag}.{f}") for f in GP_FIELDS), st))
-        check(lib.cbf_noise_backward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
-                                     at(gl.var_x), at(gl.var_y), gat("var_x_unc"), gat("var_y_unc"), st))
-        self.launches += 6 + self._nb * (1 + self._packs) + self._packs + 3
+        if d.half:
+            sc = ptr(self._scratch64)
+            check(lib.cbf_noise_backward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_x_unc")),
+                                         at(gl.var_x), at(gl.var_x), gat("var_x_unc"), sc, st))
+            check(lib.cbf_noise_backward(d.dim_y, ptr(self.view("var_y_unc")), ptr(self.view("var_y_unc")),
+                                         at(gl.var_y), at(gl.var_y), gat("var_y_unc"), sc, st))
+        else:
+            check(lib.cbf_noise_backward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
+                                         at(gl.var_x), at(gl.var_y), gat("var_x_unc"), gat("var_y_unc"), st))
+        self.launches += 6 + self._nb * (1 + self._packs) + self._packs + (3 if not d.half else 4)
         return self.grad
 
     def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -278,7 +320,7 @@ class ElboEngine:
         shape, d = self._shape, self.dims
         nb = shape.n_local // d.samples
         xf = torch.empty(nb, shape.T, d.samples, d.dim_x, dtype=F32, device=self.device)
-        yt = torch.empty_like(xf)
+        yt = None if d.half else torch.empty_like(xf)       # CBFSSMHALF has no y_tilde
         check(self.lib.cbf_export_states(C.byref(shape), ptr(y), ptr(xf), ptr(yt), ptr(self._ws), self._stream()))
         return xf, yt
 
@@ -300,7 +342,7 @@ class ElboEngine:
         gl, g, d = self._gl, self._gflat, self.dims
         M, din = d.ind_pnt_num, d.dim_in
         out = {}
-        for tag, dout in (("f", d.dim_x), ("b", d.dim_h)):
+        for tag, dout in ((("f", d.dim_x),) if d.half else (("f", d.dim_x), ("b", d.dim_h))):
             for nm, shp in (("P", (M, M)), ("alpha", (M, dout)), ("S", (M, dout)), ("Z", (M, din)),
                             ("ell", (din,)), ("sig2", (1,))):
                 off = getattr(gl, f"{tag}_{nm}")

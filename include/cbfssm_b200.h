@@ -68,6 +68,9 @@ typedef struct cbf_shape {
  * latency per time step).  These flags select them regardless of the particle count. */
 #define CBF_FLAG_FORCE_REGISTER 4
 #define CBF_FLAG_FORCE_TENSOR_CORES 8
+/* CBFSSMHALF (cbfssm/model/cbfssmhalf.py): no backward-message GP, x_0 supplied by the caller's
+ * recognition model, only the first dy state dims are conditioned.  Use the *_half entry points. */
+#define CBF_FLAG_HALF_MODEL 32
 
 
 /* Kernel-level operands of one sparse GP (gp_tf.py:103-130), float32, produced by
@@ -127,6 +130,22 @@ CBF_API int cbf_elbo_backward(const cbf_shape *shape, const cbf_gp *gp_f, const 
                       const float *eps_b, const float *z_b, const float *eps_f,
                       const double *term_weights_host,
                       double *grad_flat, void *workspace, void *stream);
+
+/* CBFSSMHALF variants (shape->flags must contain CBF_FLAG_HALF_MODEL; sequence-aligned shards only).
+ * Replace the forward while_loop + loss of cbfssmhalf.py:97-193 and tf.gradients through it.
+ * x0 [B, dx] float32: output of the recognition model (cbfssmhalf.py:64-95), tiled over the particles
+ * inside; var_y: dx floats of which the first dy are used; terms[2] (entropy) is 0.
+ * cbf_elbo_backward_half additionally returns x0_bar [n_local/S, dx] float64 = d loss / d x0 of this
+ * shard's sequences; the gp_b block of grad_flat is zero. */
+CBF_API int cbf_elbo_forward_half(const cbf_shape *shape, const cbf_gp *gp_f,
+                          const float *var_x, const float *var_y,
+                          const float *u, const float *y, const float *x0, const float *eps_f,
+                          double *terms, void *workspace, void *stream);
+CBF_API int cbf_elbo_backward_half(const cbf_shape *shape, const cbf_gp *gp_f,
+                           const float *var_x, const float *var_y,
+                           const float *u, const float *y, const float *x0, const float *eps_f,
+                           const double *term_weights_host,
+                           double *grad_flat, double *x0_bar, void *workspace, void *stream);
 
 /* x_final [B?,T,S,dx] / y_tilde in the reference layout (cbfssm.py:97,181) for this
  * shard: out tensors are [n_local/S, T, S, dx] when the shard is sequence-aligned,

@@ -1,0 +1,108 @@
+"""CBFSSMHALF through the C ABI against its float64 oracle (oracle/cbfssmhalf_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cbfssm_oracle as O
+from oracle import cbfssmhalf_oracle as H
+from tests.helpers import make_problem, rel_inf
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+CASES = [
+    # dx du dy  M   S  B   T  R  kap  cond
+    (4, 2, 2, 7, 3, 2, 11, 3, 2.0, True),
+    (4, 2, 2, 20, 40, 3, 30, 8, 1.0, True),
+    (4, 1, 1, 20, 16, 2, 25, 5, 10.0, False),
+    (4, 1, 1, 100, 10, 2, 20, 6, 1.0, True),
+    (14, 7, 7, 33, 5, 2, 12, 3, 50.0, True),
+]
+
+
+def _problem(dx, du, dy, M, S, B, T, R, kap, seed=5):
+    cfg, _, u, y, _, _, eps_f = make_problem(dx, du, dy, M, S, B, T, R, kap, (10.0, 0.0), seed=seed, strong=True)
+    return cfg, H.init_params_half(cfg, seed), u, y, eps_f
+
+
+@pytest.mark.parametrize("flags", [12, 1], ids=["register_or_tensor", "cooperative"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "dx%d_du%d_dy%d_M%d_S%d_B%d_T%d_R%d" % c[:8])
+def test_half_elbo_and_gradients_match_oracle(case, flags):
+    from cbf_ssm_b200.engine import ElboEngine, ModelDims
+    dx, du, dy, M, S, B, T, R, kap, cond = case
+    cfg, params, u, y, eps_f = _problem(dx, du, dy, M, S, B, T, R, kap)
+    g = np.random.default_rng(9)
+    x0 = np.concatenate((y[:, 0, :], 0.3 * g.standard_normal((B, dx - dy))), axis=1)   # generic x_0
+    res, gd = H.loss_and_grads_half(cfg, params, u, y, torch.tensor(x0), eps_f, cond)
+
+    eng = ElboEngine(ModelDims(dx, du, dy, M, S, R, kap, (10.0, 0.0), half=True))
+    eng.flags = flags
+    eng.set_params({k: v.numpy() for k, v in params.items()})
+    dev = eng.device
+    f32 = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+    ud, yd = f32(u), f32(y)
+    out = eng.forward(ud, yd, None, None, f32(eps_f.reshape(T - 1, B * S)), cond, x0=f32(x0))
+    eng.backward()
+    torch.cuda.synchronize()
+    for k in ("loss", "loglik", "kl_x", "kl_z_f"):
+        ref, got = float(res[k].detach()), float(out[k])
+        assert abs(got - ref) <= TOL * max(abs(ref), 1e-3), (k, got, ref)
+    assert float(out["entropy"]) == 0.0
+    xf, _ = eng.export_states(yd)
+    pm, pv = eng.moments(xf, dy, eng.var_y)
+    torch.cuda.synchronize()
+    assert rel_inf(xf.cpu().numpy(), res["x_final"].detach().numpy()) < TOL
+    assert rel_inf(pm.cpu().numpy(), res["pred_mean"].detach().numpy()) < TOL
+    assert rel_inf(pv.cpu().numpy(), res["pred_var"].detach().numpy()) < TOL
+    grads = eng.get_grads()
+    bad = {k: rel_inf(grads[k], gd[k].numpy()) for k in H.HALF_PARAM_NAMES}
+    bad = {k: v for k, v in bad.items() if not v < TOL}
+    assert not bad, bad
+    assert rel_inf(eng.x0_bar.cpu().numpy(), gd["x0"].numpy()) < TOL
+
+
+def test_half_model_rnn_recognition_and_training(tmp_path):
+    """CBFSSMHALF(config) with the default GRU recognition model: x_0 and the recognition-weight
+    gradient match the oracle composite; Trainer runs and the loss goes down."""
+    from cbf_ssm_b200.datasets import SpringNonlinearSynthetic
+    from cbf_ssm_b200.model import CBFSSMHALF, Session
+    from cbf_ssm_b200.training import Trainer
+
+    class SmallSpring(SpringNonlinearSynthetic):
+        exp_len = 400
+    ds = SmallSpring(30, 15, seed=1)
+    dim_x = 4
+    config = {'ds': SmallSpring, 'batch_size': 6, 'shuffle': 1, 'dim_x': dim_x, 'ind_pnt_num': 20, 'samples': 8,
+              'learning_rate': 0.01, 'loss_factors': np.asarray([10., 0.]), 'k_factor': 1., 'recog_len': 10,
+              'zeta_pos': 2., 'zeta_mean': 0.1 ** 2, 'zeta_var': 0.01 ** 2, 'var_x': np.asarray([0.1 ** 2] * dim_x),
+              'var_y': np.asarray([1. ** 2] * SmallSpring.dim_y), 'gp_var': 0.1 ** 2, 'gp_len': 1.}
+    model = CBFSSMHALF(config, seed=3)
+    u, y = ds.train_in_batch[:6], ds.train_out_batch[:6]
+    B, T = u.shape[0], u.shape[1]
+    eps_f = np.random.default_rng(0).standard_normal((T - 1, B, 8))
+    # oracle composite: GRU recognition -> rollout -> loss, autograd through both
+    cfg = O.OracleConfig(dim_x=dim_x, dim_u=1, dim_y=1, ind_pnt_num=20, samples=8, recog_len=10, k_factor=1.0,
+                         loss_factors=(10.0, 0.0), var_y=np.ones(dim_x))
+    params = {k: torch.tensor(v) for k, v in model.engine.get_params().items()}
+    w = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.phi_views().items()}
+    x0 = H.recog_rnn(w, u, y, 10)
+    res = H.elbo_half(cfg, params, u, y, x0, eps_f, True)
+    gw = torch.autograd.grad(res["loss"], list(w.values()))
+    # product
+    model.inject_draws(eps_f)
+    x0_gpu = model.recognise(torch.tensor(u, dtype=torch.float32, device=model.engine.device),
+                             torch.tensor(y, dtype=torch.float32, device=model.engine.device))
+    assert rel_inf(x0_gpu.detach().cpu().numpy(), x0.detach().numpy()) < 1e-6
+    loss = model.evaluate_batch(u, y, ["train", "loss"], True)[1]
+    assert float(loss) == pytest.approx(float(res["loss"].detach()), rel=1e-4)
+    got = model.phi_views(model.phi_grad)
+    for (k, _), g in zip(w.items(), gw):
+        assert rel_inf(got[k].cpu().numpy(), g.numpy()) < 1e-4, k
+    # training loop through the reference-shaped interface
+    trainer = Trainer(model, str(tmp_path))
+    trainer.train(ds, 3, verbose=False)
+    assert trainer.train_all[-1] < trainer.train_all[0]
+    sess = Session(model)
+    model.load_ds(sess, ds.test_in_batch[:1], ds.test_out_batch[:1])
+    pm, pv = sess.run((model.pred_mean, model.pred_var), {model.condition: False})
+    assert pm.shape == (1, 30, 1) and np.all(pv > 0)

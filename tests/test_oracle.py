@@ -148,3 +148,63 @@ def test_oracle_reproduces_golden(name):
     for k in O.PARAM_NAMES:
         assert rel_inf(gd[k].numpy(), gold["grad." + k]) < 1e-8, k
     assert rel_inf(res.pred_mean.detach().numpy(), gold["pred_mean"]) < 1e-10
+
+
+# --------------------------------------------------------------------------------------
+# CBFSSMHALF oracle (oracle/cbfssmhalf_oracle.py)
+# --------------------------------------------------------------------------------------
+def test_half_oracle_gradients_match_finite_differences():
+    from oracle import cbfssmhalf_oracle as H
+    cfg, _, u, y, _, _, ef = make_problem(4, 2, 2, 5, 2, 2, 7, 2, 3.0, (6.0, 0.0), seed=8, strong=True)
+    params = H.init_params_half(cfg, 8)
+    x0 = torch.tensor(np.random.default_rng(1).standard_normal((2, 4)))
+    _, gd = H.loss_and_grads_half(cfg, params, u, y, x0, ef, True)
+    rng = np.random.default_rng(0)
+    h = 1e-6
+    for name in H.HALF_PARAM_NAMES:
+        flat = params[name].reshape(-1)
+        for idx in rng.choice(flat.numel(), size=min(2, flat.numel()), replace=False):
+            vals = []
+            for sgn in (+1, -1):
+                p2 = {k: v.clone() for k, v in params.items()}
+                p2[name].reshape(-1)[idx] += sgn * h
+                vals.append(float(H.elbo_half(cfg, p2, u, y, x0, ef, True)["loss"]))
+            assert (vals[0] - vals[1]) / (2 * h) == pytest.approx(float(gd[name].reshape(-1)[idx]), rel=2e-5, abs=1e-6)
+    for idx in (0, 5):
+        vals = []
+        for sgn in (+1, -1):
+            x2 = x0.clone()
+            x2.reshape(-1)[idx] += sgn * h
+            vals.append(float(H.elbo_half(cfg, params, u, y, x2, ef, True)["loss"]))
+        assert (vals[0] - vals[1]) / (2 * h) == pytest.approx(float(gd["x0"].reshape(-1)[idx]), rel=2e-5, abs=1e-6)
+
+
+def test_half_unconditioned_dims_have_zero_kl_and_follow_the_prior():
+    """cbfssmhalf.py:144-149: dims >= dim_y get k = 0, so with dim_y conditioned dims masked out the step is
+    the GP prior step; with condition=False after recog_len-1 steps KL_x stops growing."""
+    from oracle import cbfssmhalf_oracle as H
+    cfg, _, u, y, _, _, ef = make_problem(3, 1, 1, 4, 2, 1, 6, 2, 1.0, (10.0, 0.0), seed=3, strong=True)
+    params = H.init_params_half(cfg, 3)
+    x0 = H.recog_output(y, 3)
+    assert x0.shape == (1, 3) and float(x0[0, 1]) == 0.0 and float(x0[0, 0]) == pytest.approx(float(y[0, 0, 0]))
+    a = H.elbo_half(cfg, params, u, y, x0, ef, True)
+    b = H.elbo_half(cfg, params, u, y, x0, ef, False)
+    assert float(b["kl_x"]) < float(a["kl_x"])          # only t < recog_len - 1 contribute when not conditioning
+
+
+def test_tf_gru_cell_restatement_one_step_by_hand():
+    from oracle import cbfssmhalf_oracle as H
+    g = torch.Generator().manual_seed(0)
+    d, Hn = 2, 16
+    w = {"gates_kernel": torch.randn(d + Hn, 2 * Hn, generator=g, dtype=O.DT), "gates_bias": torch.ones(2 * Hn, dtype=O.DT),
+         "candidate_kernel": torch.randn(d + Hn, Hn, generator=g, dtype=O.DT), "candidate_bias": torch.zeros(Hn, dtype=O.DT),
+         "dense_kernel": torch.eye(Hn, 3, dtype=O.DT), "dense_bias": torch.zeros(3, dtype=O.DT)}
+    u = torch.randn(1, 4, 1, generator=g, dtype=O.DT)
+    y = torch.randn(1, 4, 1, generator=g, dtype=O.DT)
+    out = H.recog_rnn(w, u, y, 1)                       # one step from h = 0 on [u_0, y_0]
+    x = torch.cat((u[:, 0], y[:, 0]), dim=1)
+    gates = torch.sigmoid(x @ w["gates_kernel"][:d] + 1.0)
+    z = gates[:, Hn:]
+    c = torch.tanh(x @ w["candidate_kernel"][:d])       # r * h = 0
+    h = (1 - z) * c
+    assert torch.allclose(out, h[:, :3], rtol=1e-12)
