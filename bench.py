@@ -295,8 +295,16 @@ def run_b200(args):
     all_flops = sum(kflops) * psteps_local
     step_frac = all_flops / (ms_per_step * 1e-3) / 1e12 / simt_peak
     bytes_pstep = 2 * (4 * dx + 8 * dh + 12)
+    traffic = None            # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
+        ent = tr.get(args.workload, {})
+        if ent.get("batch") == B:
+            traffic = ent.get(knames[dom])
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "fp32_simt", "kernel": knames[dom], "achieved": achieved, "peak": simt_peak,
-                "unit": "TFLOP/s", "frac": achieved / simt_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / simt_peak, "traffic": traffic,
                 "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({how} MEASURED_PEAKS.json); the path is FP32-SIMT "
                                "compute-bound (SURVEY 8d), not HBM- or tensor-bound",
                 "flops_per_particle_step": {k: v for k, v in zip(knames, kflops)},

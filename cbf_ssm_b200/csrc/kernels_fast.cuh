@@ -17,7 +17,10 @@
 
 namespace cbf {
 
-constexpr int kFastThreads = 128;
+#ifndef CBF_FAST_THREADS
+#define CBF_FAST_THREADS 128
+#endif
+constexpr int kFastThreads = CBF_FAST_THREADS;
 constexpr int kFastWarps = kFastThreads / 32;
 #ifndef CBF_REV_MINBLOCKS
 #define CBF_REV_MINBLOCKS 3
@@ -34,6 +37,12 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 // so without it the compiler hoists / CSEs hundreds of shared loads out of the time loop
 // (and from the first contraction into the second) and then spills them.
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+// Pull the line holding *p into L1 ahead of the next time step's dependent load (no register cost).
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#ifdef CBF_PREFETCH
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 
 // 2^x as one MUFU.EX2 (exp2f() adds range scaling: two FMULs and a predicate per call).
 // The argument is -0.5*log2(e)*d^2 + log2(sigma^2) <= log2(sigma^2); results below the
@@ -767,6 +776,9 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
 #pragma unroll 1
     for (int t = D.T - 2; t >= 0; --t) {
     compiler_fence();
+#ifdef CBF_STEP_SYNC
+    __syncthreads();
+#endif
       float x[DX], xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DX], fv[DX], yt[DX];
       const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
 #pragma unroll
@@ -781,6 +793,16 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
         for (int j = 0; j < DH; ++j) yt[DY + j] = D.half ? 0.f : Hp[j * np];
       }
       const float e = eps_f[(size_t)t * D.n_local + nr];
+      if (t > 0) {   // next iteration's (t-1) particle-major operands
+#pragma unroll
+        for (int j = 0; j < DX; ++j) prefetch_l1(Xp + ((ptrdiff_t)j - DX) * (ptrdiff_t)np);
+        if (!D.half) {
+          const float *Hn = ws.H + (((size_t)writer_run(t, D.R) * D.T + t) * DH) * np + nr;
+#pragma unroll
+          for (int j = 0; j < DH; ++j) prefetch_l1(Hn + j * np);
+        }
+        prefetch_l1(eps_f + (size_t)(t - 1) * D.n_local + nr);
+      }
       gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
       const bool do_cond = D.condition || (t < D.R - 1);
       float fmb[DX], fvb[DX], ytb[DX];
@@ -878,6 +900,9 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) bm_reverse_fa
 #pragma unroll 1
     for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
     compiler_fence();
+#ifdef CBF_STEP_SYNC
+    __syncthreads();
+#endif
       float hid[DH], xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DH], fv[DH];
       if (t == ch.t_hi) {
         const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
@@ -895,6 +920,17 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) bm_reverse_fa
 #pragma unroll
       for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
       const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
+      if (t < ch.t_hi) {   // next iteration's (t+1) particle-major operands
+        if (t + 1 < ch.t_hi) {
+          const float *Hn = ws.H + (((size_t)ch.run * D.T + (t + 2)) * DH) * np + nr;
+#pragma unroll
+          for (int j = 0; j < DH; ++j) prefetch_l1(Hn + j * np);
+        }
+        prefetch_l1(eps_b + ((size_t)ch.run * D.T + t + 1) * D.n_local + nr);
+        const float *Yn = ws.Yb + ((size_t)(t + 1) * DH) * np + nr;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) prefetch_l1(Yn + j * np);
+      }
       gp_forward_fast<M, DIN, DH, 1>(g, xin, xt, k, a, fm, fv);
       const bool write = writer_run(t, D.R) == ch.run;
       float ob[DH], fvb[DH];
