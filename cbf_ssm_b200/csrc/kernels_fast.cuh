@@ -97,8 +97,7 @@ __device__ __forceinline__ unsigned long long ffma2_bcast(float ax, float ay, fl
 // alpha and S through broadcast shared loads made the register path shared-memory bound
 // (~77 % of shared-pipe cycles).  With CBF_CONST_OPERANDS the packed operands of the GP a
 // kernel uses live in a __constant__ array instead and every use is an FFMA/FADD with a
-// c[bank][imm] operand: no load instruction and no shared-memory traffic.  P is stored as its
-// upper triangle (it is symmetric) to keep the working set inside the 2 KB constant L1.
+// c[bank][imm] or uniform-register operand: no shared-memory traffic.
 // The array is per translation unit; it is refreshed before each launch by a device-to-device
 // cudaMemcpyToSymbolAsync on the caller's stream (see launch_fast.cuh), so calls of one
 // instantiation must not overlap on different streams.
@@ -111,13 +110,11 @@ static __constant__ float c_ops[2][kConstFloats];      // [0] forward-rollout GP
 
 template <int SLOT, int M, int DIN, int DOUT>
 struct CO {
-  static constexpr int oP = 0, oZ = M * (M + 1) / 2, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT;
+  static constexpr int MP = (M + 3) / 4 * 4;   // row stride of P: rows start 16-byte aligned (LDCU.128)
+  static constexpr int oP = 0, oZ = M * MP, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT;
   static constexpr int oSig = oI + DIN, oLs = oSig + 1, TOTAL = oLs + 1;
   static_assert(TOTAL <= kConstFloats, "operands exceed the constant slot");
-  static __device__ __forceinline__ float P(int m, int mp) {   // symmetric, upper triangle
-    const int a = m < mp ? m : mp, b = m < mp ? mp : m;
-    return c_ops[SLOT][oP + a * M - a * (a - 1) / 2 + (b - a)];
-  }
+  static __device__ __forceinline__ float P(int m, int mp) { return c_ops[SLOT][oP + m * MP + mp]; }
   static __device__ __forceinline__ float Zt(int m, int j) { return c_ops[SLOT][oZ + m * DIN + j]; }
   static __device__ __forceinline__ float al(int m, int d) { return c_ops[SLOT][oA + m * DOUT + d]; }
   static __device__ __forceinline__ float S(int m, int d) { return c_ops[SLOT][oS + m * DOUT + d]; }
@@ -126,13 +123,15 @@ struct CO {
   static __device__ __forceinline__ float lsig() { return c_ops[SLOT][oLs]; }
 };
 
-// Packs one GP's operands in the CO<> layout (runtime sizes) into global scratch.
+// Packs one GP's operands in the CO<> layout (runtime sizes) into global scratch.  P is symmetrised
+// and its rows are zero-padded to MP columns.
 static __global__ void pack_const_kernel(GpDev g, int M, int DIN, int DOUT, float *__restrict__ out) {
-  const int oZ = M * (M + 1) / 2, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT, oSig = oI + DIN;
+  const int MP = (M + 3) / 4 * 4;
+  const int oZ = M * MP, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT, oSig = oI + DIN;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  for (int i = tid; i < M * M; i += nt) {
-    const int a = i / M, b = i % M;
-    if (a <= b) out[a * M - a * (a - 1) / 2 + (b - a)] = 0.5f * (g.P[a * M + b] + g.P[b * M + a]);
+  for (int i = tid; i < M * MP; i += nt) {
+    const int a = i / MP, b = i % MP;
+    out[i] = (b < M) ? 0.5f * (g.P[a * M + b] + g.P[b * M + a]) : 0.f;
   }
   for (int i = tid; i < M * DIN; i += nt) out[oZ + i] = g.Z[i] / g.ell[i % DIN];
   for (int i = tid; i < M * DOUT; i += nt) { out[oA + i] = g.alpha[i]; out[oS + i] = g.S[i]; }
@@ -140,29 +139,27 @@ static __global__ void pack_const_kernel(GpDev g, int M, int DIN, int DOUT, floa
   if (tid == 0) { out[oSig] = g.sig2[0]; out[oSig + 1] = log2f(g.sig2[0]); }
 }
 
-// a = P k with P from the constant bank (upper triangle, each off-diagonal value feeds two FMAs).
+// a = P k with P from the constant bank.  Two output rows per FFMA2: the accumulator pair
+// (a_2i, a_2i+1) takes the constant pair (P[mp][2i], P[mp][2i+1]) (= column pair of the symmetric P,
+// fetched four at a time by LDCU.128 into uniform registers) times the broadcast k[mp]:
+// M*MP/2 FFMA2 + M*MP/4 LDCU instead of M*M FFMA.
 // With ADD_BASE the result starts from base[] (a += P k), which lets the caller fold an
 // axpy into the contraction and end the live range of its operand early.
 template <int SLOT, int M, int DIN, int DOUT, int MP, bool ADD_BASE = false>
 __device__ __forceinline__ void matvec_const(const float (&k)[MP], float (&a)[MP]) {
   using C = CO<SLOT, M, DIN, DOUT>;
+  static_assert(MP == C::MP, "padded sizes must agree");
+  unsigned long long acc[MP / 2];
 #pragma unroll
-  for (int m = 0; m < MP; ++m) {
-    const float d = (m < M) ? C::P(m < M ? m : 0, m < M ? m : 0) * k[m] : 0.f;
-    a[m] = ADD_BASE ? a[m] + d : d;
+  for (int i = 0; i < MP / 2; ++i) acc[i] = ADD_BASE ? pack2(a[2 * i], a[2 * i + 1]) : 0ull;
+#pragma unroll
+  for (int mp = 0; mp < M; ++mp) {
+#pragma unroll
+    for (int i = 0; i < (M + 1) / 2; ++i)
+      acc[i] = ffma2_bcast(C::P(mp, 2 * i), C::P(mp, 2 * i + 1), k[mp], acc[i]);
   }
-  // rectangular loops with a compile-time predicate: unrolls fully, the dead half folds away
 #pragma unroll
-  for (int m = 0; m < M; ++m) {
-#pragma unroll
-    for (int mp = 0; mp < M; ++mp) {
-      if (mp > m) {
-        const float p = C::P(m, mp);
-        a[m] = fmaf(p, k[mp], a[m]);
-        a[mp] = fmaf(p, k[m], a[mp]);
-      }
-    }
-  }
+  for (int i = 0; i < MP / 2; ++i) unpack2(acc[i], a[2 * i], a[2 * i + 1]);
 }
 
 // Shared-memory image of one GP's operands, compile-time sizes.
@@ -776,9 +773,9 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
 #pragma unroll 1
     for (int t = D.T - 2; t >= 0; --t) {
     compiler_fence();
-#ifdef CBF_STEP_SYNC
+    // The loop body (~68 KB of SASS) exceeds the 32 KB L1.5 instruction cache; keeping the CTA's warps
+    // within one step of each other lets them share fetched lines (measured -7.6 % kernel time).
     __syncthreads();
-#endif
       float x[DX], xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DX], fv[DX], yt[DX];
       const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
 #pragma unroll
