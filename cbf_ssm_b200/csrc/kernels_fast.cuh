@@ -85,6 +85,26 @@ __device__ __forceinline__ unsigned long long pack2(float x, float y) {
 __device__ __forceinline__ void unpack2(unsigned long long v, float &x, float &y) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
 }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float hsum2(unsigned long long v) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+  return x + y;
+}
 __device__ __forceinline__ unsigned long long ffma2_bcast(float ax, float ay, float s, unsigned long long c) {
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack2(ax, ay)), "l"(pack2(s, s)), "l"(c));
@@ -111,30 +131,48 @@ static __constant__ float c_ops[2][kConstFloats];      // [0] forward-rollout GP
 template <int SLOT, int M, int DIN, int DOUT>
 struct CO {
   static constexpr int MP = (M + 3) / 4 * 4;   // row stride of P: rows start 16-byte aligned (LDCU.128)
-  static constexpr int oP = 0, oZ = M * MP, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT;
+  static constexpr int DINE = (DIN + 1) / 2 * 2, DOUTE = (DOUT + 1) / 2 * 2;   // even row strides: pair operands
+  static constexpr int oP = 0, oZ = M * MP, oA = oZ + M * DINE, oS = oA + M * DOUTE, oI = oS + M * DOUTE;
   static constexpr int oSig = oI + DIN, oLs = oSig + 1, TOTAL = oLs + 1;
   static_assert(TOTAL <= kConstFloats, "operands exceed the constant slot");
   static __device__ __forceinline__ float P(int m, int mp) { return c_ops[SLOT][oP + m * MP + mp]; }
-  static __device__ __forceinline__ float Zt(int m, int j) { return c_ops[SLOT][oZ + m * DIN + j]; }
-  static __device__ __forceinline__ float al(int m, int d) { return c_ops[SLOT][oA + m * DOUT + d]; }
-  static __device__ __forceinline__ float S(int m, int d) { return c_ops[SLOT][oS + m * DOUT + d]; }
+  // pair j2 of row m of -Z/ell (zero padded), alpha, S: operands of FADD2 / FFMA2
+  static __device__ __forceinline__ unsigned long long nZ2(int m, int j2) {
+    return pack2(c_ops[SLOT][oZ + m * DINE + 2 * j2], c_ops[SLOT][oZ + m * DINE + 2 * j2 + 1]);
+  }
+  static __device__ __forceinline__ unsigned long long al2(int m, int d2) {
+    return pack2(c_ops[SLOT][oA + m * DOUTE + 2 * d2], c_ops[SLOT][oA + m * DOUTE + 2 * d2 + 1]);
+  }
+  static __device__ __forceinline__ unsigned long long S2(int m, int d2) {
+    return pack2(c_ops[SLOT][oS + m * DOUTE + 2 * d2], c_ops[SLOT][oS + m * DOUTE + 2 * d2 + 1]);
+  }
+  static __device__ __forceinline__ float nZ(int m, int j) { return c_ops[SLOT][oZ + m * DINE + j]; }
+  static __device__ __forceinline__ float al(int m, int d) { return c_ops[SLOT][oA + m * DOUTE + d]; }
+  static __device__ __forceinline__ float S(int m, int d) { return c_ops[SLOT][oS + m * DOUTE + d]; }
   static __device__ __forceinline__ float il(int j) { return c_ops[SLOT][oI + j]; }
   static __device__ __forceinline__ float sig2() { return c_ops[SLOT][oSig]; }
   static __device__ __forceinline__ float lsig() { return c_ops[SLOT][oLs]; }
 };
 
 // Packs one GP's operands in the CO<> layout (runtime sizes) into global scratch.  P is symmetrised
-// and its rows are zero-padded to MP columns.
+// and its rows are zero-padded to MP columns; Z is stored negated and scaled (-Z/ell).
 static __global__ void pack_const_kernel(GpDev g, int M, int DIN, int DOUT, float *__restrict__ out) {
-  const int MP = (M + 3) / 4 * 4;
-  const int oZ = M * MP, oA = oZ + M * DIN, oS = oA + M * DOUT, oI = oS + M * DOUT, oSig = oI + DIN;
+  const int MP = (M + 3) / 4 * 4, DINE = (DIN + 1) / 2 * 2, DOUTE = (DOUT + 1) / 2 * 2;
+  const int oZ = M * MP, oA = oZ + M * DINE, oS = oA + M * DOUTE, oI = oS + M * DOUTE, oSig = oI + DIN;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int i = tid; i < M * MP; i += nt) {
     const int a = i / MP, b = i % MP;
     out[i] = (b < M) ? 0.5f * (g.P[a * M + b] + g.P[b * M + a]) : 0.f;
   }
-  for (int i = tid; i < M * DIN; i += nt) out[oZ + i] = g.Z[i] / g.ell[i % DIN];
-  for (int i = tid; i < M * DOUT; i += nt) { out[oA + i] = g.alpha[i]; out[oS + i] = g.S[i]; }
+  for (int i = tid; i < M * DINE; i += nt) {
+    const int m = i / DINE, j = i % DINE;
+    out[oZ + i] = (j < DIN) ? -g.Z[m * DIN + j] / g.ell[j] : 0.f;
+  }
+  for (int i = tid; i < M * DOUTE; i += nt) {
+    const int m = i / DOUTE, d = i % DOUTE;
+    out[oA + i] = (d < DOUT) ? g.alpha[m * DOUT + d] : 0.f;
+    out[oS + i] = (d < DOUT) ? g.S[m * DOUT + d] : 0.f;
+  }
   for (int i = tid; i < DIN; i += nt) out[oI + i] = 1.f / g.ell[i];
   if (tid == 0) { out[oSig] = g.sig2[0]; out[oSig + 1] = log2f(g.sig2[0]); }
 }
@@ -250,19 +288,27 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
   constexpr int MP = G::MP, DINP = G::DINP, DOUTP = G::DOUTP;
   if constexpr (kConstOps) {
     using C = typename G::C;
+    constexpr int J2 = C::DINE / 2, D2 = C::DOUTE / 2;
 #pragma unroll
     for (int j = 0; j < DINP; ++j) xt[j] = (j < DIN) ? xin[j < DIN ? j : 0] * C::il(j < DIN ? j : 0) : 0.f;
+    unsigned long long x2[J2], fm2[D2], fv2[D2];
 #pragma unroll
-    for (int d = 0; d < DOUT; ++d) fm[d] = 0.f;
+    for (int j = 0; j < J2; ++j) x2[j] = pack2(xt[2 * j], xt[2 * j + 1]);
+#pragma unroll
+    for (int d = 0; d < D2; ++d) { fm2[d] = 0ull; fv2[d] = 0ull; }
 #pragma unroll
     for (int m = 0; m < MP; ++m) {
       if (m < M) {
-        float d2 = 0.f;
+        unsigned long long acc = 0ull;   // (sum over even j, sum over odd j) of delta^2
 #pragma unroll
-        for (int j = 0; j < DIN; ++j) { const float e = xt[j] - C::Zt(m < M ? m : 0, j); d2 = fmaf(e, e, d2); }
-        k[m] = fast_exp2(fmaf(kNegHalfLog2e, d2, g.lsig));
+        for (int j = 0; j < J2; ++j) {
+          const unsigned long long dl = add2(x2[j], C::nZ2(m < M ? m : 0, j));
+          acc = fma2(dl, dl, acc);
+        }
+        k[m] = fast_exp2(fmaf(kNegHalfLog2e, hsum2(acc), g.lsig));
+        const unsigned long long kk = pack2(k[m], k[m]);
 #pragma unroll
-        for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(k[m], C::al(m < M ? m : 0, d), fm[d]);
+        for (int d = 0; d < D2; ++d) fm2[d] = fma2(C::al2(m < M ? m : 0, d), kk, fm2[d]);
       } else {
         k[m] = 0.f;
       }
@@ -270,16 +316,21 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
     matvec_const<SLOT, M, DIN, DOUT, MP>(k, a);
     float q = 0.f;
 #pragma unroll
-    for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
-#pragma unroll
     for (int m = 0; m < M; ++m) {
       q = fmaf(k[m], a[m], q);
       const float a2 = a[m] * a[m];
+      const unsigned long long aa = pack2(a2, a2);
 #pragma unroll
-      for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, C::S(m, d), fv[d]);
+      for (int d = 0; d < D2; ++d) fv2[d] = fma2(C::S2(m, d), aa, fv2[d]);
     }
 #pragma unroll
-    for (int d = 0; d < DOUT; ++d) fv[d] = g.sig2 - q + fv[d];
+    for (int d = 0; d < D2; ++d) {
+      float m0, m1, v0, v1;
+      unpack2(fm2[d], m0, m1);
+      unpack2(fv2[d], v0, v1);
+      fm[2 * d] = m0; fv[2 * d] = g.sig2 - q + v0;
+      if (2 * d + 1 < DOUT) { fm[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = m1; fv[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = g.sig2 - q + v1; }
+    }
     return;
   }
   {
@@ -472,6 +523,45 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
 #pragma unroll
     for (int m = 0; m < MP; ++m) pb[m] = -Gs * a[m];
     matvec_const<SLOT, M, DIN, DOUT, MP, true>(b, pb);
+#ifdef CBF_PACKED_DELTA
+    constexpr int J2 = C::DINE / 2, N2 = (NEED + 1) / 2;
+    unsigned long long x2[J2], xs2[N2], L2[J2];   // packed over input-dim pairs (2j, 2j+1)
+#pragma unroll
+    for (int j = 0; j < J2; ++j) { x2[j] = pack2(xt[2 * j], xt[2 * j + 1]); L2[j] = 0ull; }
+#pragma unroll
+    for (int j = 0; j < N2; ++j) xs2[j] = 0ull;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float kb = 2.f * pb[m];
+#pragma unroll
+      for (int d = 0; d < DOUT; ++d) kb = fmaf(C::al(m, d), gm[d], kb);
+      const float w = kb * k[m];
+      sw += w;
+      const unsigned long long ww = pack2(w, w);
+#pragma unroll
+      for (int j = 0; j < J2; ++j) {
+        const unsigned long long dl = add2(x2[j], C::nZ2(m, j));
+        const unsigned long long wd = mul2(dl, ww);
+        if (j < N2) xs2[j < N2 ? j : 0] = add2(xs2[j < N2 ? j : 0], wd);
+        L2[j] = fma2(wd, dl, L2[j]);
+      }
+      W::put_left(stg, lane, W::L_W, m, w);
+    }
+#pragma unroll
+    for (int j = 0; j < J2; ++j) {
+      float l0, l1;
+      unpack2(L2[j], l0, l1);
+      Lacc[2 * j] += l0;
+      if (2 * j + 1 < DIN) Lacc[2 * j + 1 < DIN ? 2 * j + 1 : 0] += l1;
+    }
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+      float s0, s1;
+      unpack2(xs2[j], s0, s1);
+      xinb[2 * j] = -s0;
+      if (2 * j + 1 < NEED) xinb[2 * j + 1 < NEED ? 2 * j + 1 : 0] = -s1;
+    }
+#else
 #pragma unroll
     for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
 #pragma unroll
@@ -483,13 +573,14 @@ __device__ __forceinline__ void gp_reverse_fast(const GpF<M, DIN, DOUT, SLOT> &g
       sw += w;
 #pragma unroll
       for (int j = 0; j < DIN; ++j) {
-        const float dl = xt[j] - C::Zt(m, j);
+        const float dl = xt[j] + C::nZ(m, j);
         const float wd = w * dl;
         if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
         Lacc[j] = fmaf(wd, dl, Lacc[j]);
       }
       W::put_left(stg, lane, W::L_W, m, w);
     }
+#endif
     W::template put_right<DOUT, DOUT>(stg, lane, W::colGm, gm);
     W::template put_right<DOUT, DOUT>(stg, lane, W::colGv, gv);
     {
