@@ -186,3 +186,48 @@ def test_model_and_trainer_follow_the_reference_interface(tmp_path):
     model.load_ds(sess, ds.test_in_batch, ds.test_out_batch)
     losses = model.run(sess, model.loss, {model.condition: True})
     assert losses[0].shape == (-(-ds.test_in_batch.shape[0] // 8),)   # list of per-fetch arrays (base_model.py:54)
+
+
+def test_outputs_writes_the_reference_report_files(tmp_path):
+    """cbfssm/outputs/outputs.py:36-164 on a tiny .mat-backed problem: predict_*.mat, mse.txt, var_dump.txt."""
+    import scipy.io
+    from cbf_ssm_b200.datasets import SpringNonlinear, create_spring_nonlinear
+    from cbf_ssm_b200.model import CBFSSM
+    from cbf_ssm_b200.outputs import Outputs
+    from cbf_ssm_b200.training import Trainer
+
+    data = str(tmp_path / "data") + "/"
+    os.makedirs(data)
+    create_spring_nonlinear(data + "spring_nonlinear.mat", ds_size=10000, seed=0)
+
+    class DS(SpringNonlinear):
+        def __init__(self, seq_len, seq_stride):
+            super().__init__(seq_len, seq_stride, data_path=data)
+    ds = DS(100, 500)
+    dim_x = 4
+    config = {'ds': DS, 'batch_size': 8, 'shuffle': 10000, 'dim_x': dim_x, 'ind_pnt_num': 20, 'samples': 16,
+              'learning_rate': 0.01, 'loss_factors': np.asarray([10., 0.]), 'k_factor': 1., 'recog_len': 10,
+              'zeta_pos': 2., 'zeta_mean': 0.1 ** 2, 'zeta_var': 0.01 ** 2, 'var_x': np.asarray([0.1 ** 2] * dim_x),
+              'var_y': np.asarray([1. ** 2] * dim_x), 'gp_var': 0.1 ** 2, 'gp_len': 1., 'shuffle_seed': 0}
+    model = CBFSSM(config, seed=0)
+    model_dir, out_dir = str(tmp_path / "model"), str(tmp_path / "out")
+    trainer = Trainer(model, model_dir)
+    trainer.train(ds, 2, verbose=False)
+    out = Outputs(out_dir)
+    out.set_ds(ds)
+    out.set_model(model, model_dir)
+    out.set_trainer(trainer)
+    out.create_all()
+    for split in ("train", "test"):
+        m = scipy.io.loadmat(os.path.join(out_dir, "predict_%s.mat" % split))
+        assert m["mean"].shape == (300, 1) and m["std"].shape == (300, 1) and m["gt"].shape == (300, 1)
+        assert np.all(m["std"] > 0) and np.all(np.isfinite(m["mean"]))
+    lines = open(os.path.join(out_dir, "mse.txt")).read().split()
+    assert lines[0] == "MSE:" and lines[2] == "RMSE:" and float(lines[3]) == pytest.approx(out.get_last_rmse(), abs=1e-6)
+    assert float(lines[3]) == pytest.approx(np.sqrt(float(lines[1])), rel=1e-4)
+    dump = open(os.path.join(out_dir, "var_dump.txt")).read()
+    for name in model.var_dict:
+        assert name + ":\n" in dump
+    block = dump.split("IP pos f:\n")[1].split("\n\n")[0].strip().split("\n")
+    assert len(block) == 20 and len(block[0].split()) == dim_x + 1      # [M, dx + du] rows
+    assert np.loadtxt(os.path.join(out_dir, "training_loss.txt")).shape == (2, 3)

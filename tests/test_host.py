@@ -158,3 +158,56 @@ def test_load_ds_and_run_follow_the_reference_iterator_semantics():
     _, idx4 = model3.run(Session(model3), (model3.loss, model3.idx), {})
     assert sorted(idx4.tolist()) == list(range(n))
     assert all(v <= i + 2 for i, v in enumerate(idx4.tolist()))   # bounded look-ahead of a size-3 buffer
+
+
+# --------------------------------------------------------------------------------------
+# on-disk dataset format: ds_manager.py:11-34, dsmanager_ds.py:6-63
+# --------------------------------------------------------------------------------------
+def test_mat_files_round_trip_and_feed_the_dataset_classes(tmp_path):
+    import scipy.io
+    from cbf_ssm_b200.datasets import (DSManager, RoboMove, RoboMoveSimple, SpringNonlinear, create_robomove,
+                                       create_spring_nonlinear)
+    d = str(tmp_path) + "/"
+    u, x, y = create_spring_nonlinear(d + "spring_nonlinear.mat", seed=3)
+    assert u.shape == (10000, 1) and x.shape == (10000, 3) and y.shape == (10000, 3)
+    raw = scipy.io.loadmat(d + "spring_nonlinear.mat")           # the keys the reference reads
+    assert {"ds_u", "ds_x", "ds_y", "title"} <= set(raw) and raw["ds_u"].dtype == np.float64
+    u2, x2, y2 = DSManager.load_ds(d + "spring_nonlinear.mat", print_title=False)
+    assert np.array_equal(u, u2) and np.array_equal(x, x2) and np.array_equal(y, y2)
+    # x_{i+1} = f(x_i, u_i): the spring's linear recursion holds between consecutive rows
+    A = np.array([[1.0, 0.01, 0.0], [0.0, 1.0, 0.01], [-500.0, -25.0, 0.0]])
+    assert np.allclose(x[1:], x[:-1] @ A.T + np.outer(np.tanh(2 * u[:-1, 0]), [0, 0, 500.0]), atol=1e-9)
+    un = DSManager.normalize_ds(u)
+    assert np.allclose(un.mean(0), 0, atol=1e-12) and np.allclose(un.std(0), 1)
+
+    ds = SpringNonlinear(100, 50, data_path=d)                  # y_crop=1, split 5000, stride 50 -> 99 windows
+    assert ds.train_in.shape == (1, 5000, 1) and ds.train_out.shape == (1, 5000, 1)
+    assert ds.train_in_batch.shape == (99, 100, 1) and ds.test_out_batch.shape == (99, 100, 1)
+    whole = np.concatenate((ds.train_out[0], ds.test_out[0]))   # statistics are those of the whole file
+    assert np.allclose(whole.mean(0), 0, atol=1e-9) and np.allclose(whole.std(0), 1)
+    assert np.allclose(ds.denormalize(ds.train_out[0], 'out')[:, 0], y[:5000, 0])
+
+    create_robomove(d + "robomove.mat", ds_size=30000, seed=1)
+    rm = RoboMove(300, 50, data_path=d)
+    assert (rm.dim_u, rm.dim_y) == (2, 2) and rm.train_in_batch.shape == (495, 300, 2)   # SURVEY 8d cfg 2
+    assert rm.test_in_batch.shape == (95, 300, 2)
+    create_robomove(d + "robomove_simple.mat", ds_size=26000, seed=2, simple=True)
+    rs = RoboMoveSimple(300, 50, data_path=d)
+    assert rs.train_out_batch.shape == (495, 300, 4) and rs.test_out.shape == (1, 1000, 4)
+    with pytest.raises(AssertionError):
+        DSManager.save_ds(d + "bad.mat", u[:5], x, y, "bad")
+
+
+def test_unicycle_generator_obeys_its_kinematics():
+    """create_robomove.py:22-52: a step of length s on a circle of curvature c turns the heading by s*c and
+    moves the robot along the chord; straight motion for |c| < 1e-5."""
+    from cbf_ssm_b200.datasets.mat_ds import _Unicycle
+    rob = _Unicycle(np.random.default_rng(0), 0.0, 0.0, simple=False)
+    rob.propagate([0.5, 0.0])
+    assert np.allclose(rob.get_state(), [0.0, 0.5, 0.0])        # heading 0 points along +y
+    start = rob.pos.copy()
+    for _ in range(8):                                           # 8 steps of an eighth of a unit circle
+        rob.propagate([2 * np.pi / 8, 1.0])
+    assert np.allclose(rob.pos, start, atol=1e-12) and rob.angle == pytest.approx(0.0, abs=1e-12)
+    rob.propagate([np.pi / 2, 1.0])                              # quarter turn to the right
+    assert np.allclose(rob.pos - start, [1.0, 1.0]) and rob.angle == pytest.approx(np.pi / 2)
