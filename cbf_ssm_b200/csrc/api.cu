@@ -122,6 +122,12 @@ constexpr int kOuterMaxGrid = 148 * 2;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Bytes of one GP's outer-product operand tiles (common.cuh TcMats) for `cols` columns.
+static size_t mats_bytes(size_t cols, int M, int dout, int din) {
+  const size_t rb = (size_t)4 * ceil_div(M, 8) + 2 * ceil_div(dout, 8) + ceil_div(din + 1, 8);
+  return ((cols + kOT - 1) / kOT) * 2 * rb * kOBlk;
+}
+
 static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   if (!s) { set_error("shape is NULL"); return CBF_ERR_NULL; }
   if (s->B < 1 || s->S < 1 || s->T < 1 || s->M < 1 || s->dx < 2 || s->du < 0 || s->dy < 1 || s->dy >= s->dx ||
@@ -194,9 +200,8 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
     p.colsb = (size_t)live * s->n_local;
     p.ctot_f = s->M + 2 * p.dx + p.din + 1;
     p.ctot_b = s->M + 2 * p.dh + p.din + 1;
-    const size_t rows_f = (size_t)4 * s->M + 2 * p.dx + p.din + 1, rows_b = (size_t)4 * s->M + 2 * p.dh + p.din + 1;
-    const size_t blkf = (p.colsf + 15) / 16, blkb = (p.colsb + 15) / 16;
-    const size_t bytes = sizeof(float) * 16 * (rows_f * blkf + rows_b * blkb);
+    const size_t bytes_f = mats_bytes(p.colsf, s->M, p.dx, p.din), bytes_b = mats_bytes(p.colsb, s->M, p.dh, p.din);
+    const size_t bytes = bytes_f + bytes_b;
     p.tc_rev = p.tc_fwd && p.ops->fw_reverse_tc != nullptr && p.ops->smem_tc(s->M, 2) <= kMaxSmem &&
                p.ops->smem_tc(s->M, 3) <= kMaxSmem && bytes <= kTcMaxMatBytes && p.colsf > 0 && (p.colsb > 0 || p.half) &&
                p.colsf < ((size_t)1 << 31) && p.colsb < ((size_t)1 << 31);
@@ -206,8 +211,8 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
       const int pt = ceil_div(s->n_local, 128);
       p.nspart_f = pt;
       p.nspart_b = pt * (int)p.chains.size();
-      p.off_mf = o; o = align_up(o + sizeof(float) * 16 * rows_f * blkf, 256);
-      p.off_mb = o; o = align_up(o + sizeof(float) * 16 * rows_b * blkb, 256);
+      p.off_mf = o; o = align_up(o + bytes_f, 256);
+      p.off_mb = o; o = align_up(o + bytes_b, 256);
       p.off_rpart = o; o = align_up(o + sizeof(double) * (size_t)kOuterMaxGrid * 128 * kOCols, 256);
       p.off_spf = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_f * p.nsc_f, 256);
       p.off_spb = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_b * p.nsc_b, 256);
@@ -223,12 +228,20 @@ static int device_sms();
 
 static TcMats bind_mats(void *base, size_t off, size_t L, int M, int dout, int din) {
   TcMats m;
-  m.blk = reinterpret_cast<float *>(static_cast<char *>(base) + off);
+  m.blk = reinterpret_cast<unsigned char *>(base) + off;
   m.L = L;
-  m.rAb = 0; m.rK = M; m.rA2 = 2 * M; m.rW = 3 * M;
-  m.rGm = 4 * M; m.rGv = 4 * M + dout; m.rX1 = 4 * M + 2 * dout;
-  m.R = 4 * M + 2 * dout + din + 1;
+  m.MB = ceil_div(M, 8); m.DB = ceil_div(dout, 8); m.XB = ceil_div(din + 1, 8);
+  m.RB = 4 * m.MB + 2 * m.DB + m.XB;
+  m.bAb = 0; m.bK = m.MB; m.bA2 = 2 * m.MB; m.bW = 3 * m.MB;
+  m.bGm = 4 * m.MB; m.bGv = m.bGm + m.DB; m.bX1 = m.bGv + m.DB;
   return m;
+}
+
+// The reverse kernels write only the L valid columns; the bulk copies of the accumulation kernel read whole
+// tiles, so the unwritten tail of the last tile is cleared first.
+static cudaError_t clear_mats_tail(const TcMats &m, cudaStream_t st) {
+  if (m.L == 0 || m.L % kOT == 0) return cudaSuccess;
+  return cudaMemsetAsync(m.blk + (m.L / kOT) * m.tile_bytes(), 0, m.tile_bytes(), st);
 }
 
 // P_bar', alpha_bar', S_bar, [U|r] of one GP on the tensor cores (kernels_outer.cuh) -> Rd [M x Ctot] float64.
@@ -679,12 +692,14 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
 
   const int nch = (int)p.chains.size();
   if (p.tc_rev) {
-    // ---- tensor-core path: rollout adjoints on tcgen05, parameter outer products as chunked SGEMMs ----
+    // ---- tensor-core path: rollout adjoints on tcgen05, parameter outer products as a tcgen05 split-K stream ----
     char *wb = static_cast<char *>(workspace);
     const TcMats mf = bind_mats(workspace, p.off_mf, p.colsf, p.D.M, p.dx, p.din);
     const TcMats mb = bind_mats(workspace, p.off_mb, p.colsb, p.D.M, p.dh, p.din);
     float *spf = reinterpret_cast<float *>(wb + p.off_spf), *spb = reinterpret_cast<float *>(wb + p.off_spb);
     double *rdf = reinterpret_cast<double *>(wb + p.off_rdf), *rdb = reinterpret_cast<double *>(wb + p.off_rdb);
+    CBF_CUDA(clear_mats_tail(mf, st));
+    if (!p.half) CBF_CUDA(clear_mats_tail(mb, st));
     {
       ScopedTiming tm(2, st);
       CBF_CUDA(p.ops->fw_reverse_tc(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, mf, spf, p.nsc_f, st));

@@ -33,19 +33,24 @@ struct GpDev {
   const float *Z, *ell, *sig2, *P, *alpha, *S;
 };
 
-// Outer-product operands one tensor-path reverse kernel writes for one GP (float32), in a
-// tile-major layout: the L = (live steps x particles) columns are cut into blocks of 16 and each block
-// into four 4-column chunks; a block holds, chunk by chunk, all R rows' 16-byte segments contiguously:
-// element (row, col) at  blk[(col/16)*R*16 + ((col%16)/4)*R*4 + row*4 + col%4].
-// Rows: a_bar (M) | k' (M) | a^2 (M) | w (M) | g_mean (Dout) | g_var (Dout) | [x~, 1] (Din+1).
-// The accumulation kernel reads one block as a single contiguous ~26 KB stream whose float4 index is
-// (chunk, row) -- exactly the order of the UMMA K-major core-matrix layout it stages it into, so both
-// its global loads and its shared stores are conflict-free and coalesced.
+// Outer-product operands one tensor-path reverse kernel writes for one GP, already in the form the
+// accumulation GEMM (kernels_outer.cuh) consumes: every value x is stored as two bfloat16 terms
+// hi = rn(x), lo = rn(x - hi) (16 significant bits together), and the L = (live steps x particles)
+// columns are cut into tiles of kOT.  A tile is a sequence of row-blocks; one row-block holds 8 rows x kOT
+// columns as kOT 16-byte segments (segment c = the 8 rows' values of column c): the MN-major,
+// no-swizzle core-matrix layout of tcgen05 (8 columns x 16 bytes = one 128-byte core matrix), so a tile
+// is copied to shared memory by plain bulk copies and a writing thread (one column) stores 16 bytes per
+// 8 rows.  Parts, hi copies first: a_bar | k' | a^2 | w (MB blocks each) | g_mean | g_var (DB) | [x~,1] (XB);
+// the lo copy of a part sits RB blocks after its hi copy.  Rows beyond a part's size are written as zeros.
+constexpr int kOT = 32;                 // columns per tile (two k-steps of 16)
+constexpr int kOBlk = kOT * 16;         // bytes of one row-block
 struct TcMats {
-  float *blk;
+  unsigned char *blk;
   size_t L;        // valid columns
-  int R;           // rows per block
-  int rAb, rK, rA2, rW, rGm, rGv, rX1;
+  int MB, DB, XB;  // row-blocks of an M-row part, of g_mean / g_var, of [x~,1]
+  int RB;          // row-blocks per half tile = 4 MB + 2 DB + XB
+  int bAb, bK, bA2, bW, bGm, bGv, bX1;   // first (hi) row-block of each part
+  __host__ __device__ size_t tile_bytes() const { return (size_t)2 * RB * kOBlk; }
 };
 
 // Device views into the caller's workspace.

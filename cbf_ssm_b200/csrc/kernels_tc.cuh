@@ -19,9 +19,11 @@
 // a = P k and the second contraction P b on the tensor core (b is scaled per particle by a power
 // of two into fp16 range and split the same way), the step adjoint and the k_bar / x_bar chain in
 // SIMT, and writes the operands of the parameter-adjoint outer products (a_bar, k, a^2, w, g_mean,
-// g_var, x~) as float32 rows of a tile-major matrix (common.cuh TcMats) to the workspace; the accumulation
-// over (particle, step) is the tcgen05 split-K reduction of kernels_outer.cuh.
+// g_var, x~) as bfloat16 hi/lo pairs in the MMA-ready tile layout of common.cuh TcMats to the workspace
+// (16 bytes per 8 rows per thread, fully coalesced); the accumulation over (particle, step) is the
+// tcgen05 split-K reduction of kernels_outer.cuh.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "kernels_fast.cuh"
@@ -257,14 +259,64 @@ __device__ __forceinline__ void tc_write_row8(__half *b1, __half *b2, int ch, co
   *reinterpret_cast<uint4 *>(b2 + off) = v2;
 }
 
+// x = hi + lo with two bfloat16 terms (round-to-nearest each): 8 values -> two 16-byte segments.
+__device__ __forceinline__ void split_bf16x8(const float (&v)[8], uint4 &hi, uint4 &lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    h[e] = *reinterpret_cast<const uint32_t *>(&hh);
+    const float h0 = __uint_as_float(h[e] << 16), h1 = __uint_as_float(h[e] & 0xFFFF0000u);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * e] - h0, v[2 * e + 1] - h1);
+    l[e] = *reinterpret_cast<const uint32_t *>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// This particle-step's column of the outer-product operand tile (common.cuh TcMats): row-block r of the
+// tile is at col + r * kOBlk, its lo copy RB blocks further.
+struct TcOut {
+  unsigned char *col;
+  int RB, MB, DB, XB;
+  int bAb, bK, bA2, bW, bGm, bGv, bX1;
+  __device__ __forceinline__ void put8(int blk, const float (&v)[8]) const {
+    uint4 hi, lo;
+    split_bf16x8(v, hi, lo);
+    *reinterpret_cast<uint4 *>(col + (size_t)blk * kOBlk) = hi;
+    *reinterpret_cast<uint4 *>(col + (size_t)(blk + RB) * kOBlk) = lo;
+  }
+  __device__ __forceinline__ void get8(int blk, float (&v)[8]) const {
+    const uint4 hi = *reinterpret_cast<const uint4 *>(col + (size_t)blk * kOBlk);
+    const uint4 lo = *reinterpret_cast<const uint4 *>(col + (size_t)(blk + RB) * kOBlk);
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(h[e] << 16) + __uint_as_float(l[e] << 16);
+      v[2 * e + 1] = __uint_as_float(h[e] & 0xFFFF0000u) + __uint_as_float(l[e] & 0xFFFF0000u);
+    }
+  }
+  // n values (n <= 8 * nblk) as nblk row-blocks starting at blk, zero padded
+  template <int N>
+  __device__ __forceinline__ void put_vec(int blk, const float (&v)[N]) const {
+#pragma unroll
+    for (int r = 0; r < (N + 7) / 8; ++r) {
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = (8 * r + e < N) ? v[8 * r + e < N ? 8 * r + e : 0] : 0.f;
+      put8(blk + r, w);
+    }
+  }
+};
+
 // One sparse-GP evaluation (gp_tf.py:132-161) for the CTA's 128 particles; every thread must call.
-// kout (optional): float32 matrix row pointer [m][ldk] receiving k' for the outer-product GEMMs.
+// kout (optional): operand-tile column receiving k' for the outer-product GEMMs.
 // amax: max_m |a''_m| of this particle's normalised accumulator row (scales b in the reverse pass);
 // kscale: the particle's normalisation, k' = kscale * k''.
 template <class Ctx, int DIN, int DOUT>
 __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], float (&xt)[(DIN + 3) / 4 * 4],
-                                              float (&fm)[DOUT], float (&fv)[DOUT], float *__restrict__ kout,
-                                              size_t ldk, float &amax, float &kscale) {
+                                              float (&fm)[DOUT], float (&fv)[DOUT], const TcOut *kout,
+                                              float &amax, float &kscale) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   constexpr int MC = Ctx::MC;
   const int t = threadIdx.x, M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
@@ -320,11 +372,16 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
         ld_row<DOUTP>(c.al + m * DOUTP, al);
 #pragma unroll
         for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(kp, al[d], fm[d]);
-        if (kout) kout[(size_t)m * ldk] = kscale * kp;
       }
       kv[e] = kp;
     }
     tc_write_row8(c.K1, c.K2, ch, kv);
+    if (kout && ch < kout->MB) {
+      float ks[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ks[e] = kscale * kv[e];
+      kout->put8(kout->bK + ch, ks);
+    }
   }
   // ---- D1 = K P' on the tensor core ----
   tc_contract(c, c.K1, c.K2, c.tmem);
@@ -363,13 +420,6 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   tc_fence_before();   // order this step's tcgen05.ld before the next barrier / MMA
 }
 
-// Destination rows (float32, [row][ld], this particle's column already applied) of the
-// outer-product operands one reverse evaluation writes.
-struct TcOut {
-  float *K, *Ab, *A2, *W, *Gm, *Gv, *X1;
-  size_t ld;
-};
-
 // Reverse of one GP evaluation (SURVEY 8a note 4) on the tile; follows gp_forward_tc of the same step
 // (K1/K2 and the accumulator D1 still hold k' and a').  gm/gv: adjoints of (fmean, fvar).
 template <class Ctx, int DIN, int DOUT, int NEED>
@@ -392,22 +442,24 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   const float bsc = ldexpf(1.f, -e2), binv = ldexpf(1.f, e2);
   const uint32_t trow1 = c.tmem + ((uint32_t)(t & ~31) << 16), trow2 = trow1 + 128;
   if (live) {
+    o.template put_vec<DOUT>(o.bGm, gm);
+    o.template put_vec<DOUT>(o.bGv, gv);
+    float x1[DIN + 1];
 #pragma unroll
-    for (int d = 0; d < DOUT; ++d) { o.Gm[(size_t)d * o.ld] = gm[d]; o.Gv[(size_t)d * o.ld] = gv[d]; }
-#pragma unroll
-    for (int j = 0; j < DIN; ++j) o.X1[(size_t)j * o.ld] = xt[j];
-    o.X1[(size_t)DIN * o.ld] = 1.f;
+    for (int j = 0; j < DIN; ++j) x1[j] = xt[j];
+    x1[DIN] = 1.f;
+    o.template put_vec<DIN + 1>(o.bX1, x1);
   }
   // ---- b'' = a' (S gv) 2^-e -> fp16 split rows of B ----
 #pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16];
     tmem_ld16(trow1 + cc * 16, a);
-    float bv[16];
+    float bv[16], a2[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
-      float b = 0.f;
+      float b = 0.f, asq = 0.f;
       if (m < M) {
         float S[DOUTP];
         ld_row<DOUTP>(c.Sm + m * DOUTP, S);
@@ -415,15 +467,23 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 #pragma unroll
         for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], gv[d], cm);
         b = a[e] * cm * bsc;
-        if (live) { const float at = ascale * a[e]; o.A2[(size_t)m * o.ld] = at * at; }
+        const float at = ascale * a[e];
+        asq = at * at;
       }
       bv[e] = b;
+      a2[e] = asq;
     }
     float lo[8], hi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { lo[e] = bv[e]; hi[e] = bv[8 + e]; }
     tc_write_row8(c.B1, c.B2, 2 * cc, lo);
     tc_write_row8(c.B1, c.B2, 2 * cc + 1, hi);
+    if (live) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { lo[e] = a2[e]; hi[e] = a2[8 + e]; }
+      if (2 * cc < o.MB) o.put8(o.bA2 + 2 * cc, lo);
+      if (2 * cc + 1 < o.MB) o.put8(o.bA2 + 2 * cc + 1, hi);
+    }
   }
   tc_fence_before();
   // ---- D2 = B P' ----
@@ -439,8 +499,16 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     tmem_ld16(trow2 + cc * 16, pb);
     tmem_ld16(trow1 + cc * 16, a);
     tc_read_row16(c.B1, c.B2, cc, bb);
+    {   // true k' (hi + lo terms of the column this thread wrote during the forward evaluation)
+      float k0[8], k1[8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) kp[e] = (live && cc * 16 + e < M) ? o.K[(size_t)(cc * 16 + e) * o.ld] : 0.f;   // true k'
+      for (int e = 0; e < 8; ++e) { k0[e] = 0.f; k1[e] = 0.f; }
+      if (live && 2 * cc < o.MB) o.get8(o.bK + 2 * cc, k0);
+      if (live && 2 * cc + 1 < o.MB) o.get8(o.bK + 2 * cc + 1, k1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { kp[e] = k0[e]; kp[8 + e] = k1[e]; }
+    }
+    float wv[16], abv[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
@@ -462,11 +530,23 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
           if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
           Lacc[j] = fmaf(wd, dl, Lacc[j]);
         }
-        if (live) {
-          o.W[(size_t)m * o.ld] = w;
-          o.Ab[(size_t)m * o.ld] = 2.f * bs * bb[e] - Gs * k;
-        }
+        wv[e] = w;
+        abv[e] = 2.f * bs * bb[e] - Gs * k;
+      } else {
+        wv[e] = 0.f;
+        abv[e] = 0.f;
       }
+    }
+    if (live) {
+      float lo[8], hi[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { lo[e] = wv[e]; hi[e] = wv[8 + e]; }
+      if (2 * cc < o.MB) o.put8(o.bW + 2 * cc, lo);
+      if (2 * cc + 1 < o.MB) o.put8(o.bW + 2 * cc + 1, hi);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { lo[e] = abv[e]; hi[e] = abv[8 + e]; }
+      if (2 * cc < o.MB) o.put8(o.bAb + 2 * cc, lo);
+      if (2 * cc + 1 < o.MB) o.put8(o.bAb + 2 * cc + 1, hi);
     }
   }
   {
@@ -522,7 +602,7 @@ __global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, Chain
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
     float xt[TcCtx<DIN, DH>::DINP], amax, kscale;
-    gp_forward_tc<TcCtx<DIN, DH, false, MC>, DIN, DH>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
+    gp_forward_tc<TcCtx<DIN, DH, false, MC>, DIN, DH>(c, xin, xt, fm, fv, nullptr, amax, kscale);
     const bool write = writer_run(t, D.R) == ch.run;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
@@ -599,7 +679,7 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
     load_ytil(t + 1, yt);
     const float e = eps_f[(size_t)t * D.n_local + nr];
     float xt[TcCtx<DIN, DX>::DINP], amax, kscale;
-    gp_forward_tc<TcCtx<DIN, DX, false, MC>, DIN, DX>(c, xin, xt, fm, fv, nullptr, 0, amax, kscale);
+    gp_forward_tc<TcCtx<DIN, DX, false, MC>, DIN, DX>(c, xin, xt, fm, fv, nullptr, amax, kscale);
     const bool do_cond = D.condition || (t < D.R - 1);
     fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, xn, kl);
 #pragma unroll
@@ -615,12 +695,10 @@ __global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev
 }
 
 __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
-  const unsigned c = (unsigned)(col & 15);
-  float *b = m.blk + (col >> 4) * ((size_t)m.R * 16) + (size_t)(c >> 2) * ((size_t)m.R * 4) + (c & 3);
   TcOut o;
-  o.Ab = b + m.rAb * 4; o.K = b + m.rK * 4; o.A2 = b + m.rA2 * 4; o.W = b + m.rW * 4;
-  o.Gm = b + m.rGm * 4; o.Gv = b + m.rGv * 4; o.X1 = b + m.rX1 * 4;
-  o.ld = 4;
+  o.col = m.blk + (col / kOT) * m.tile_bytes() + (size_t)(col % kOT) * 16;
+  o.RB = m.RB; o.MB = m.MB; o.DB = m.DB; o.XB = m.XB;
+  o.bAb = m.bAb; o.bK = m.bK; o.bA2 = m.bA2; o.bW = m.bW; o.bGm = m.bGm; o.bGv = m.bGv; o.bX1 = m.bX1;
   return o;
 }
 
@@ -684,7 +762,7 @@ __global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev
     }
     const float e = eps_f[(size_t)t * D.n_local + nr];
     const TcOut o = tc_out_at(mats, (size_t)t * D.n_local + nr);
-    gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? o.K : nullptr, o.ld, amax, kscale);
+    gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale);
     const bool do_cond = D.condition || (t < D.R - 1);
     float fmb[DX], fvb[DX], ytb[DX];
     fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
@@ -780,7 +858,7 @@ __global__ void __launch_bounds__(kTcThreads) bm_reverse_tc_kernel(Dims D, Chain
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
     const TcOut o = tc_out_at(mats, ((size_t)ch.col0 + (t - ch.t_lo)) * D.n_local + nr);
-    gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, live ? o.K : nullptr, o.ld, amax, kscale);
+    gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale);
     const bool write = writer_run(t, D.R) == ch.run;
     float ob[DH], fvb[DH];
     const float *Yp = ws.Yb + ((size_t)t * DH) * np + nr;
