@@ -35,11 +35,13 @@ import numpy as np
 METRIC = "elbo_fwd_bwd_particle_steps_per_sec"
 UNIT = "particle-steps/s"
 WORKLOADS = {
-    # BASELINE.json configs[1]: the headline workload (default)
-    "robomove_m20": dict(dx=4, du=2, dy=2, M=20, S=50, T=300, R=50, kap=1.0, lf=(20.0, 0.0), batch=4096,
+    # BASELINE.json configs[1]: the headline workload (default).  Batches are sized to whole waves of the
+    # kernels' resident CTAs (148 SMs x 3 CTAs x 128 particles for the register path, 148 x 2 x 128 for the
+    # tensor path): 4544 x 50 particles = 4.0 waves, 1515 x 50 = 2.0 waves.
+    "robomove_m20": dict(dx=4, du=2, dy=2, M=20, S=50, T=300, R=50, kap=1.0, lf=(20.0, 0.0), batch=4544,
                          name="RoboMove-shaped CBF-SSM dx4/du2/dy2 M20 S50 T300 R50 (BASELINE.json configs[1])"),
     # run/template.py defaults (north_star target shape M=100, D=4); secondary, not the driver's line
-    "template_m100": dict(dx=4, du=2, dy=2, M=100, S=50, T=100, R=50, kap=1.0, lf=(10.0, 0.0), batch=1024,
+    "template_m100": dict(dx=4, du=2, dy=2, M=100, S=50, T=100, R=50, kap=1.0, lf=(10.0, 0.0), batch=1515,
                           name="run/template.py CBF-SSM dx4/du2/dy2 M100 S50 T100 R50"),
     "sarcos_m100": dict(dx=14, du=7, dy=7, M=100, S=20, T=250, R=16, kap=50.0, lf=(6.0, 0.0), batch=512,
                         name="Sarcos-shaped CBF-SSM dx14/du7/dy7 M100 S20 T250 R16 (BASELINE.json configs[2])"),
