@@ -75,14 +75,37 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void async_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// 16 consecutive accumulator columns of this thread's TMEM lane.  The issue and the wait are separate so
+// that several loads (and independent global / shared loads) can be in flight before the first use.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Wait that carries the loaded registers as in/out operands, so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16], uint32_t (&q)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(q[0]),
+                 "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]), "+r"(q[9]),
+                 "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld16_issue(taddr, r);
+  tmem_ld_wait(r);
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -296,6 +319,27 @@ struct TcOut {
       v[2 * e + 1] = __uint_as_float(h[e] & 0xFFFF0000u) + __uint_as_float(l[e] & 0xFFFF0000u);
     }
   }
+  // raw hi/lo segments of row-blocks blk and blk+1 (zeros when absent): q = {hi0, lo0, hi1, lo1}
+  __device__ __forceinline__ void get8_raw(int blk, bool live, uint4 (&q)[4]) const {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    q[0] = q[1] = q[2] = q[3] = z;
+    if (live && blk - bK < MB) {
+      q[0] = *reinterpret_cast<const uint4 *>(col + (size_t)blk * kOBlk);
+      q[1] = *reinterpret_cast<const uint4 *>(col + (size_t)(blk + RB) * kOBlk);
+    }
+    if (live && blk + 1 - bK < MB) {
+      q[2] = *reinterpret_cast<const uint4 *>(col + (size_t)(blk + 1) * kOBlk);
+      q[3] = *reinterpret_cast<const uint4 *>(col + (size_t)(blk + 1 + RB) * kOBlk);
+    }
+  }
+  static __device__ __forceinline__ void unpack8(const uint4 &hi, const uint4 &lo, float (&v)[8]) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(h[e] << 16) + __uint_as_float(l[e] << 16);
+      v[2 * e + 1] = __uint_as_float(h[e] & 0xFFFF0000u) + __uint_as_float(l[e] & 0xFFFF0000u);
+    }
+  }
   // n values (n <= 8 * nblk) as nblk row-blocks starting at blk, zero padded
   template <int N>
   __device__ __forceinline__ void put_vec(int blk, const float (&v)[N]) const {
@@ -486,6 +530,8 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     }
   }
   tc_fence_before();
+  uint4 kq[4];   // raw hi/lo segments of two row-blocks of k' (one 16-row chunk), fetched one chunk ahead
+  o.get8_raw(o.bK, live, kq);
   // ---- D2 = B P' ----
   tc_contract(c, c.B1, c.B2, c.tmem + 128);
   // ---- k_bar = alpha gm + 2 P b - 2 G a ; w = k_bar k ; a_bar = 2 b - G k ----
@@ -496,17 +542,24 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 #pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float pb[16], a[16], kp[16], bb[16];
-    tmem_ld16(trow2 + cc * 16, pb);
-    tmem_ld16(trow1 + cc * 16, a);
-    tc_read_row16(c.B1, c.B2, cc, bb);
-    {   // true k' (hi + lo terms of the column this thread wrote during the forward evaluation)
-      float k0[8], k1[8];
+    {
+      uint32_t rp[16], ra[16];
+      tmem_ld16_issue(trow2 + cc * 16, rp);
+      tmem_ld16_issue(trow1 + cc * 16, ra);
+      // true k' of this chunk was fetched one iteration ahead; fetch the next chunk's now
+      const uint4 c0 = kq[0], c1 = kq[1], c2 = kq[2], c3 = kq[3];
+      if (cc + 1 < MP / 16) o.get8_raw(o.bK + 2 * cc + 2, live, kq);
+      tc_read_row16(c.B1, c.B2, cc, bb);
+      {
+        float k0[8], k1[8];
+        TcOut::unpack8(c0, c1, k0);
+        TcOut::unpack8(c2, c3, k1);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { k0[e] = 0.f; k1[e] = 0.f; }
-      if (live && 2 * cc < o.MB) o.get8(o.bK + 2 * cc, k0);
-      if (live && 2 * cc + 1 < o.MB) o.get8(o.bK + 2 * cc + 1, k1);
+        for (int e = 0; e < 8; ++e) { kp[e] = k0[e]; kp[8 + e] = k1[e]; }
+      }
+      tmem_ld_wait(rp, ra);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { kp[e] = k0[e]; kp[8 + e] = k1[e]; }
+      for (int e = 0; e < 16; ++e) { pb[e] = __uint_as_float(rp[e]); a[e] = __uint_as_float(ra[e]); }
     }
     float wv[16], abv[16];
 #pragma unroll
@@ -707,7 +760,7 @@ __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
 // Per-CTA output: scalar sums [L_j | sum w | sum G | var_x_bar | var_y_bar] at spart[cta].
 // =====================================================================================
 template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+__global__ void __launch_bounds__(kTcThreads, 2) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -745,12 +798,22 @@ __global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev
     for (int j = 0; j < DX; ++j)
       xb[j] = (j < DY && live) ? w_ll * (yb[(D.T - 1) * DY + (j < DY ? j : 0)] - Xp[j * np]) / vy[j] : 0.f;
   }
+  float xnext[DX];   // x_t of the coming iteration, fetched one step ahead (it heads the step's dependency chain)
+  {
+    const float *Xp = ws.X + ((size_t)(D.T > 1 ? D.T - 2 : 0) * DX) * np + nr;
+#pragma unroll
+    for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
+  }
 #pragma unroll 1
   for (int t = D.T - 2; t >= 0; --t) {
     float x[DX], xin[DIN], xt[Ctx::DINP], fm[DX], fv[DX], yt[DX], amax, kscale;
-    const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
 #pragma unroll
-    for (int j = 0; j < DX; ++j) { x[j] = Xp[j * np]; xin[j] = x[j]; }
+    for (int j = 0; j < DX; ++j) { x[j] = xnext[j]; xin[j] = x[j]; }
+    if (t > 0) {
+      const float *Xp = ws.X + ((size_t)(t - 1) * DX) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
+    }
 #pragma unroll
     for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
 #pragma unroll
@@ -802,7 +865,7 @@ __global__ void __launch_bounds__(kTcThreads) fw_reverse_tc_kernel(Dims D, GpDev
 }
 
 template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+__global__ void __launch_bounds__(kTcThreads, 2) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -838,18 +901,26 @@ __global__ void __launch_bounds__(kTcThreads) bm_reverse_tc_kernel(Dims D, Chain
   float hb[DH];
 #pragma unroll
   for (int j = 0; j < DH; ++j) hb[j] = 0.f;
-#pragma unroll 1
-  for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
-    float hid[DH], xin[DIN], xt[Ctx::DINP], fm[DH], fv[DH], amax, kscale;
+  // the message state entering step t: the chain's initial value at t_hi, else the output of step t+1
+  auto load_hidden = [&](int t, float(&hv)[DH]) {
     if (t == ch.t_hi) {
       const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
 #pragma unroll
-      for (int j = 0; j < DH; ++j) hid[j] = z;
+      for (int j = 0; j < DH; ++j) hv[j] = z;
     } else {
       const float *Hp = ws.H + (((size_t)ch.run * D.T + (t + 1)) * DH) * np + nr;
 #pragma unroll
-      for (int j = 0; j < DH; ++j) hid[j] = Hp[j * np];
+      for (int j = 0; j < DH; ++j) hv[j] = Hp[j * np];
     }
+  };
+  float hnext[DH];   // fetched one step ahead (it heads the step's dependency chain)
+  load_hidden(ch.t_lo, hnext);
+#pragma unroll 1
+  for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
+    float hid[DH], xin[DIN], xt[Ctx::DINP], fm[DH], fv[DH], amax, kscale;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) hid[j] = hnext[j];
+    if (t < ch.t_hi) load_hidden(t + 1, hnext);
 #pragma unroll
     for (int j = 0; j < DH; ++j) xin[j] = hid[j];
 #pragma unroll
