@@ -435,11 +435,16 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
+  uint32_t ra[16];
+  tmem_ld16_issue(trow, ra);
 #pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16], kp[16];
-    tmem_ld16(trow + cc * 16, a);
     tc_read_row16(c.K1, c.K2, cc, kp);
+    tmem_ld_wait(ra);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) a[e] = __uint_as_float(ra[e]);
+    if (cc + 1 < MP / 16) tmem_ld16_issue(trow + (cc + 1) * 16, ra);   // next chunk in flight during this one's math
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
@@ -495,10 +500,15 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     o.template put_vec<DIN + 1>(o.bX1, x1);
   }
   // ---- b'' = a' (S gv) 2^-e -> fp16 split rows of B ----
+  uint32_t ra1[16];
+  tmem_ld16_issue(trow1, ra1);
 #pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16];
-    tmem_ld16(trow1 + cc * 16, a);
+    tmem_ld_wait(ra1);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) a[e] = __uint_as_float(ra1[e]);
+    if (cc + 1 < MP / 16) tmem_ld16_issue(trow1 + (cc + 1) * 16, ra1);
     float bv[16], a2[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -613,7 +623,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 
 // =====================================================================================
 template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+__global__ void __launch_bounds__(kTcThreads, 2) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__(kTcThreads) bm_forward_tc_kernel(Dims D, Chain
 }
 
 template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+__global__ void __launch_bounds__(kTcThreads, 2) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
