@@ -13,6 +13,7 @@ PyTorch is used for device memory, streams and ``torch.distributed`` only.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, Optional
@@ -157,6 +158,7 @@ class ElboEngine:
         self.x0_bar = None        # CBFSSMHALF: d loss / d x0 [nb, dim_x] after backward()
         self._ws = None
         self._ws_key = None
+        self._side = None
         self._gl = None
         self._gflat = None
         self._shape = None
@@ -183,6 +185,25 @@ class ElboEngine:
     # ---------------- plumbing ----------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @contextlib.contextmanager
+    def _two_gps(self):
+        """Streams (f, b) for the float64 single-CTA kernels of the two GPs.  From M = 48 the O(M^3) prologue
+        and its adjoint take 0.2-0.4 ms each and the two GPs are independent, so the backward-message GP's
+        kernel runs on a side stream next to the other one (fork / join by events); below that the kernels
+        are tens of microseconds and both stay on the caller's stream."""
+        main = torch.cuda.current_stream(self.device)
+        if self.dims.ind_pnt_num < 48 or self.dims.half:
+            yield self._stream(), self._stream()
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork.record(main)
+        self._side.wait_event(self._ev_fork)
+        yield self._stream(), C.c_void_p(self._side.cuda_stream)
+        self._ev_join.record(self._side)
+        main.wait_event(self._ev_join)
 
     def make_shape(self, B, T, condition=True, n_offset=0, n_local=None):
         d = self.dims
@@ -217,10 +238,12 @@ class ElboEngine:
         else:
             check(lib.cbf_noise_forward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
                                         ptr(self.var_x), ptr(self.var_y), st))
-        for tag, g in ((("f", self.gp_f),) if d.half else (("f", self.gp_f), ("b", self.gp_b))):
-            check(lib.cbf_gp_prologue(g.M, g.din, g.dout, *(ptr(self.view(f"{tag}.{f}")) for f in GP_FIELDS),
-                                      ptr(g.Z), ptr(g.ell), ptr(g.sig2), ptr(g.P), ptr(g.alpha), ptr(g.S),
-                                      ptr(g.kl), ptr(g.state), st))
+        with self._two_gps() as streams:
+            for tag, g, s2 in ((("f", self.gp_f, streams[0]),) if d.half else
+                               (("f", self.gp_f, streams[0]), ("b", self.gp_b, streams[1]))):
+                check(lib.cbf_gp_prologue(g.M, g.din, g.dout, *(ptr(self.view(f"{tag}.{f}")) for f in GP_FIELDS),
+                                          ptr(g.Z), ptr(g.ell), ptr(g.sig2), ptr(g.P), ptr(g.alpha), ptr(g.S),
+                                          ptr(g.kl), ptr(g.state), s2))
         self.launches += 2 if d.half else 3
 
     def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True, x0=None):
@@ -293,9 +316,10 @@ class ElboEngine:
         gps = [("f", self.gp_f, (gl.f_P, gl.f_alpha, gl.f_S, gl.f_Z, gl.f_ell, gl.f_sig2))]
         if not d.half:
             gps.append(("b", self.gp_b, (gl.b_P, gl.b_alpha, gl.b_S, gl.b_Z, gl.b_ell, gl.b_sig2)))
-        for tag, g, o in gps:
-            check(lib.cbf_gp_prologue_backward(g.M, g.din, g.dout, *(at(x) for x in o), 1.0, ptr(g.state),
-                                               *(gat(f"{tag}.{f}") for f in GP_FIELDS), st))
+        with self._two_gps() as streams:
+            for (tag, g, o), s2 in zip(gps, streams):
+                check(lib.cbf_gp_prologue_backward(g.M, g.din, g.dout, *(at(x) for x in o), 1.0, ptr(g.state),
+                                                   *(gat(f"{tag}.{f}") for f in GP_FIELDS), s2))
         if d.half:
             sc = ptr(self._scratch64)
             check(lib.cbf_noise_backward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_x_unc")),
