@@ -37,13 +37,6 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 // so without it the compiler hoists / CSEs hundreds of shared loads out of the time loop
 // (and from the first contraction into the second) and then spills them.
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
-// Pull the line holding *p into L1 ahead of the next time step's dependent load (no register cost).
-__device__ __forceinline__ void prefetch_l1(const void *p) {
-#ifdef CBF_PREFETCH
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-
 // 2^x as one MUFU.EX2 (exp2f() adds range scaling: two FMULs and a predicate per call).
 // The argument is -0.5*log2(e)*d^2 + log2(sigma^2) <= log2(sigma^2); results below the
 // float32 normal range flush to zero, which is what the kernel value is there anyway.
@@ -861,6 +854,19 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
       for (int j = 0; j < DX; ++j)
         xb[j] = (j < DY && live) ? w_ll * (yb[(D.T - 1) * DY + (j < DY ? j : 0)] - Xp[j * np]) / vy[j] : 0.f;
     }
+    // Particle-major operands of a step (x_t, y2_{t+1}, eps_t) are fetched during the previous step's
+    // accumulation phase, when few registers are live, so their HBM/L2 latency is off the critical path.
+    float xq[DX], hq[DH], eq;
+    auto fetch = [&](int t) {
+      const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) xq[j] = Xp[j * np];
+      const float *Hp = ws.H + (((size_t)writer_run(t + 1, D.R) * D.T + (t + 1)) * DH) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) hq[j] = D.half ? 0.f : Hp[j * np];
+      eq = eps_f[(size_t)t * D.n_local + nr];
+    };
+    if (D.T >= 2) fetch(D.T - 2);
 #pragma unroll 1
     for (int t = D.T - 2; t >= 0; --t) {
     compiler_fence();
@@ -868,29 +874,15 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
     // within one step of each other lets them share fetched lines (measured -7.6 % kernel time).
     __syncthreads();
       float x[DX], xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DX], fv[DX], yt[DX];
-      const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
 #pragma unroll
-      for (int j = 0; j < DX; ++j) { x[j] = Xp[j * np]; xin[j] = x[j]; }
+      for (int j = 0; j < DX; ++j) { x[j] = xq[j]; xin[j] = x[j]; }
 #pragma unroll
       for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
 #pragma unroll
       for (int j = 0; j < DY; ++j) yt[j] = yb[(t + 1) * DY + j];
-      {
-        const float *Hp = ws.H + (((size_t)writer_run(t + 1, D.R) * D.T + (t + 1)) * DH) * np + nr;
 #pragma unroll
-        for (int j = 0; j < DH; ++j) yt[DY + j] = D.half ? 0.f : Hp[j * np];
-      }
-      const float e = eps_f[(size_t)t * D.n_local + nr];
-      if (t > 0) {   // next iteration's (t-1) particle-major operands
-#pragma unroll
-        for (int j = 0; j < DX; ++j) prefetch_l1(Xp + ((ptrdiff_t)j - DX) * (ptrdiff_t)np);
-        if (!D.half) {
-          const float *Hn = ws.H + (((size_t)writer_run(t, D.R) * D.T + t) * DH) * np + nr;
-#pragma unroll
-          for (int j = 0; j < DH; ++j) prefetch_l1(Hn + j * np);
-        }
-        prefetch_l1(eps_f + (size_t)(t - 1) * D.n_local + nr);
-      }
+      for (int j = 0; j < DH; ++j) yt[DY + j] = hq[j];
+      const float e = eq;
       gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
       const bool do_cond = D.condition || (t < D.R - 1);
       float fmb[DX], fvb[DX], ytb[DX];
@@ -907,6 +899,7 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) fw_reverse_fa
       __syncwarp();   // previous step's accumulate() has finished reading the staging tile
       gp_reverse_fast<M, DIN, DX, DX, 0>(g, stg, lane, xt, k, a, fmb, fvb, live, xinb, Lacc, sw, sG);
       __syncwarp();
+      if (t > 0) fetch(t - 1);
       wacc.accumulate(stg);
 #pragma unroll
       for (int j = 0; j < DX; ++j) {
@@ -985,6 +978,25 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) bm_reverse_fa
     float hb[DH];
 #pragma unroll
     for (int j = 0; j < DH; ++j) hb[j] = 0.f;
+    // Particle-major operands of a step (message state, eps, adjoint of y2) are fetched during the previous
+    // step's accumulation phase, when few registers are live.
+    float hq[DH], yq[DH], eq;
+    auto fetch = [&](int t) {
+      if (t == ch.t_hi) {
+        const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) hq[j] = z;
+      } else {
+        const float *Hp = ws.H + (((size_t)ch.run * D.T + (t + 1)) * DH) * np + nr;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) hq[j] = Hp[j * np];
+      }
+      eq = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
+      const float *Yp = ws.Yb + ((size_t)t * DH) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) yq[j] = Yp[j * np];
+    };
+    fetch(ch.t_lo);
 #pragma unroll 1
     for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
     compiler_fence();
@@ -992,43 +1004,22 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) bm_reverse_fa
     __syncthreads();
 #endif
       float hid[DH], xin[DIN], xt[G::DINP], k[G::MP], a[G::MP], fm[DH], fv[DH];
-      if (t == ch.t_hi) {
-        const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
 #pragma unroll
-        for (int j = 0; j < DH; ++j) hid[j] = z;
-      } else {
-        const float *Hp = ws.H + (((size_t)ch.run * D.T + (t + 1)) * DH) * np + nr;
-#pragma unroll
-        for (int j = 0; j < DH; ++j) hid[j] = Hp[j * np];
-      }
-#pragma unroll
-      for (int j = 0; j < DH; ++j) xin[j] = hid[j];
+      for (int j = 0; j < DH; ++j) { hid[j] = hq[j]; xin[j] = hid[j]; }
 #pragma unroll
       for (int j = 0; j < DU; ++j) xin[DH + j] = ub[t * DU + j];
 #pragma unroll
       for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
-      const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
-      if (t < ch.t_hi) {   // next iteration's (t+1) particle-major operands
-        if (t + 1 < ch.t_hi) {
-          const float *Hn = ws.H + (((size_t)ch.run * D.T + (t + 2)) * DH) * np + nr;
-#pragma unroll
-          for (int j = 0; j < DH; ++j) prefetch_l1(Hn + j * np);
-        }
-        prefetch_l1(eps_b + ((size_t)ch.run * D.T + t + 1) * D.n_local + nr);
-        const float *Yn = ws.Yb + ((size_t)(t + 1) * DH) * np + nr;
-#pragma unroll
-        for (int j = 0; j < DH; ++j) prefetch_l1(Yn + j * np);
-      }
+      const float e = eq;
       gp_forward_fast<M, DIN, DH, 1>(g, xin, xt, k, a, fm, fv);
       const bool write = writer_run(t, D.R) == ch.run;
       float ob[DH], fvb[DH];
-      const float *Yp = ws.Yb + ((size_t)t * DH) * np + nr;
 #pragma unroll
       for (int j = 0; j < DH; ++j) {
         const float f = fv[j] + vx[j];
         float o = hb[j], fb = 0.f;
         if (write) {
-          o += Yp[j * np];
+          o += yq[j];
           fb = w_en * 0.5f / f;
         }
         fb += o * e * 0.5f * rsqrtf(f);
@@ -1040,6 +1031,7 @@ __global__ void __launch_bounds__(kFastThreads, CBF_REV_MINBLOCKS) bm_reverse_fa
       __syncwarp();
       gp_reverse_fast<M, DIN, DH, DH, 1>(g, stg, lane, xt, k, a, ob, fvb, live, xinb, Lacc, sw, sG);
       __syncwarp();
+      if (t < ch.t_hi) fetch(t + 1);
       wacc.accumulate(stg);
 #pragma unroll
       for (int j = 0; j < DH; ++j) hb[j] = xinb[j] + ob[j];
