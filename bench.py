@@ -43,7 +43,7 @@ WORKLOADS = {
     # run/template.py defaults (north_star target shape M=100, D=4); secondary, not the driver's line
     "template_m100": dict(dx=4, du=2, dy=2, M=100, S=50, T=100, R=50, kap=1.0, lf=(10.0, 0.0), batch=1515,
                           name="run/template.py CBF-SSM dx4/du2/dy2 M100 S50 T100 R50"),
-    "sarcos_m100": dict(dx=14, du=7, dy=7, M=100, S=20, T=250, R=16, kap=50.0, lf=(6.0, 0.0), batch=512,
+    "sarcos_m100": dict(dx=14, du=7, dy=7, M=100, S=20, T=250, R=16, kap=50.0, lf=(6.0, 0.0), batch=1894,
                         name="Sarcos-shaped CBF-SSM dx14/du7/dy7 M100 S20 T250 R16 (BASELINE.json configs[2])"),
 }
 WORK = dict(WORKLOADS["robomove_m20"])
