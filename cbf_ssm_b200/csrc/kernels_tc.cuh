@@ -30,7 +30,12 @@
 
 namespace cbf {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 128;   // threads (= particles = TMEM lanes) of one particle tile
+
+// Barrier over the 128 threads of one particle tile (named barrier 1 + tile; 0 is __syncthreads).
+__device__ __forceinline__ void tile_sync(int tile) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(kTcThreads) : "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -120,22 +125,30 @@ __device__ __forceinline__ void split_h(float x, __half &h1, __half &h2) {
 }
 
 // Shared-memory state of one CTA: operands, resident small GP tables, barrier, TMEM base.
-template <int DIN, int DOUT, bool REV = false, int MC_ = 0>
+// NT particle tiles per CTA (NT x 128 threads): each tile has its own operand buffers, TMEM columns, mbarrier
+// and named barrier and runs independently; the tiles share P1/P2 and the small tables.  NT = 2 is used
+// where one tile's CTA is too large for two CTAs per SM (D >= 8 at M = 100: 11-22 KB of tables), which
+// restores 8 warps per SM.
+template <int DIN, int DOUT, bool REV = false, int MC_ = 0, int NT_ = 1>
 struct TcCtx {
+  static constexpr int NT = NT_;
   static constexpr int MC = MC_;     // compile-time M (0: runtime) -- lets the M loops unroll and drop their guards
   static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   static constexpr uint32_t TMEM_COLS = REV ? 256u : 128u;
   __half *P1, *P2, *K1, *K2, *B1, *B2;
   const float *Zt, *al, *Sm, *il;
-  uint32_t bar, tmem, idesc;
+  uint32_t bar, tmem, tmem_base, idesc;
   uint32_t phase;
   int M, MP;
+  int tile_, tl_;       // (NT > 1) particle tile of this thread within the CTA, lane (= TMEM lane, operand row) in the tile
+  __device__ __forceinline__ int tile_id() const { return NT == 1 ? 0 : tile_; }
+  __device__ __forceinline__ int lane_id() const { return NT == 1 ? (int)threadIdx.x : tl_; }
   float sig2, pscale;   // P = pscale * P'
   float smax[DOUT];     // max_m S_md (bound used to scale b in the reverse pass)
 
   static size_t bytes(int M) {
     const int MP = round_up(M, 16);
-    return (size_t)2 * MP * MP * 2 + (size_t)2 * kTcThreads * MP * 2 +
+    return (size_t)2 * MP * MP * 2 + (size_t)NT * 2 * kTcThreads * MP * 2 +
            sizeof(float) * ((size_t)M * (DINP + 2 * DOUTP) + DINP + 4) + 64;
   }
 
@@ -144,8 +157,11 @@ struct TcCtx {
     M = M_; MP = round_up(M, 16);
     P1 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
     P2 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
-    K1 = reinterpret_cast<__half *>(base); base += (size_t)kTcThreads * MP * 2;
-    K2 = reinterpret_cast<__half *>(base); base += (size_t)kTcThreads * MP * 2;
+    tile_ = threadIdx.x / kTcThreads; tl_ = threadIdx.x % kTcThreads;
+    const int tile = tile_id();
+    K1 = reinterpret_cast<__half *>(base) + (size_t)(2 * tile) * kTcThreads * MP;
+    K2 = K1 + (size_t)kTcThreads * MP;
+    base += (size_t)NT * 2 * kTcThreads * MP * 2;
     // The reverse pass reuses the K operand buffers for b (k is re-read from the float32 operand
     // matrix it was just written to, an L2 hit), which keeps the CTA at ~114 KB: two CTAs per SM.
     B1 = K1; B2 = K2;
@@ -153,7 +169,7 @@ struct TcCtx {
     float *aw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
     float *Sw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
     float *iw = reinterpret_cast<float *>(base); base += sizeof(float) * (DINP + 4);
-    uint64_t *barp = reinterpret_cast<uint64_t *>(base); base += 16;
+    uint64_t *barp = reinterpret_cast<uint64_t *>(base); base += 32;   // one mbarrier per tile
     uint32_t *tmemp = reinterpret_cast<uint32_t *>(base); base += 16;
     const int tid = threadIdx.x, nt = blockDim.x;
     // scale of P: |P / 2^e| <= 1024
@@ -198,16 +214,18 @@ struct TcCtx {
 #pragma unroll
         for (int d = 0; d < DOUT; ++d) smax[d] = fmaxf(smax[d], g.S[m * DOUT + d]);
     }
-    bar = smem_u32(barp);
+    bar = smem_u32(barp + tile);
     idesc = umma_idesc_f16(128, MP);
     phase = 0;
     if (tid == 0) {
-      mbar_init(bar, 1);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) mbar_init(smem_u32(barp + q), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if (tid < 32) {   // one warp allocates the TMEM columns (fp32 accumulators, 128 lanes x MP <= 128 each)
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemp)), "r"(TMEM_COLS)
+    if (tid < 32) {   // one warp allocates the TMEM columns (fp32 accumulators, 128 lanes x MP <= 128 per tile)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemp)),
+                   "r"(TMEM_COLS * NT)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -215,7 +233,8 @@ struct TcCtx {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    tmem = *tmemp;
+    tmem_base = *tmemp;
+    tmem = tmem_base + (uint32_t)tile * TMEM_COLS;
     return base;
   }
 
@@ -223,18 +242,18 @@ struct TcCtx {
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS * NT) : "memory");
   }
 };
 
-// D[tmem_d] = A1 P1 + A2 P1 + A1 P2 for the CTA's 128 rows; all threads call (contains the CTA barrier
+// D[tmem_d] = A1 P1 + A2 P1 + A1 P2 for the tile's 128 rows; all threads of the tile call (contains the tile barrier
 // and the mbarrier wait).  a1/a2: fp16 split A operands written by the threads just before.
 template <class Ctx>
 __device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __half *a2p, uint32_t tmem_d) {
   async_proxy_fence();
   tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if (Ctx::NT == 1) __syncthreads(); else tile_sync(c.tile_id());
+  if (c.lane_id() == 0) {
     tc_fence_after();
     const uint32_t lboA = kTcThreads * 16, lboB = c.MP * 16;
     const uint32_t a1 = smem_u32(a1p), a2 = smem_u32(a2p), b1 = smem_u32(c.P1), b2 = smem_u32(c.P2);
@@ -255,10 +274,10 @@ __device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __h
 }
 
 // This thread's row (16 fp16-split values starting at column 16*cc) of an A-operand buffer pair.
-__device__ __forceinline__ void tc_read_row16(const __half *b1, const __half *b2, int cc, float (&v)[16]) {
+__device__ __forceinline__ void tc_read_row16(const __half *b1, const __half *b2, int row, int cc, float (&v)[16]) {
 #pragma unroll
   for (int hch = 0; hch < 2; ++hch) {
-    const size_t off = (size_t)(cc * 2 + hch) * (kTcThreads * 8) + threadIdx.x * 8;
+    const size_t off = (size_t)(cc * 2 + hch) * (kTcThreads * 8) + row * 8;
     const uint4 v1 = *reinterpret_cast<const uint4 *>(b1 + off);
     const uint4 v2 = *reinterpret_cast<const uint4 *>(b2 + off);
     const uint32_t w1[4] = {v1.x, v1.y, v1.z, v1.w}, w2[4] = {v2.x, v2.y, v2.z, v2.w};
@@ -271,13 +290,13 @@ __device__ __forceinline__ void tc_read_row16(const __half *b1, const __half *b2
     }
   }
 }
-__device__ __forceinline__ void tc_write_row8(__half *b1, __half *b2, int ch, const float (&v)[8]) {
+__device__ __forceinline__ void tc_write_row8(__half *b1, __half *b2, int row, int ch, const float (&v)[8]) {
   __half h1[8], h2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) split_h(v[e], h1[e], h2[e]);
   const uint4 v1 = make_uint4(pack_h2(h1[0], h1[1]), pack_h2(h1[2], h1[3]), pack_h2(h1[4], h1[5]), pack_h2(h1[6], h1[7]));
   const uint4 v2 = make_uint4(pack_h2(h2[0], h2[1]), pack_h2(h2[2], h2[3]), pack_h2(h2[4], h2[5]), pack_h2(h2[6], h2[7]));
-  const size_t off = (size_t)ch * (kTcThreads * 8) + threadIdx.x * 8;
+  const size_t off = (size_t)ch * (kTcThreads * 8) + row * 8;
   *reinterpret_cast<uint4 *>(b1 + off) = v1;
   *reinterpret_cast<uint4 *>(b2 + off) = v2;
 }
@@ -363,7 +382,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
                                               float &amax, float &kscale) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   constexpr int MC = Ctx::MC;
-  const int t = threadIdx.x, M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
+  const int t = c.lane_id(), M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
   {
     float il[DINP];
     ld_row<DINP>(c.il, il);
@@ -419,7 +438,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       }
       kv[e] = kp;
     }
-    tc_write_row8(c.K1, c.K2, ch, kv);
+    tc_write_row8(c.K1, c.K2, t, ch, kv);
     if (kout && ch < kout->MB) {
       float ks[8];
 #pragma unroll
@@ -440,7 +459,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16], kp[16];
-    tc_read_row16(c.K1, c.K2, cc, kp);
+    tc_read_row16(c.K1, c.K2, t, cc, kp);
     tmem_ld_wait(ra);
 #pragma unroll
     for (int e = 0; e < 16; ++e) a[e] = __uint_as_float(ra[e]);
@@ -478,7 +497,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
                                               float &sG) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   constexpr int MC = Ctx::MC;
-  const int t = threadIdx.x, M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
+  const int t = c.lane_id(), M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
   const float ps = c.pscale, sig2 = c.sig2;
   const float ascale = ps * sig2 * kscale;      // a = ascale * a'' (a'' = P' k'' is what D1 holds)
   float Gs = 0.f, cbound = 0.f;
@@ -530,8 +549,8 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     float lo[8], hi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { lo[e] = bv[e]; hi[e] = bv[8 + e]; }
-    tc_write_row8(c.B1, c.B2, 2 * cc, lo);
-    tc_write_row8(c.B1, c.B2, 2 * cc + 1, hi);
+    tc_write_row8(c.B1, c.B2, t, 2 * cc, lo);
+    tc_write_row8(c.B1, c.B2, t, 2 * cc + 1, hi);
     if (live) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { lo[e] = a2[e]; hi[e] = a2[8 + e]; }
@@ -559,7 +578,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       // true k' of this chunk was fetched one iteration ahead; fetch the next chunk's now
       const uint4 c0 = kq[0], c1 = kq[1], c2 = kq[2], c3 = kq[3];
       if (cc + 1 < MP / 16) o.get8_raw(o.bK + 2 * cc + 2, live, kq);
-      tc_read_row16(c.B1, c.B2, cc, bb);
+      tc_read_row16(c.B1, c.B2, t, cc, bb);
       {
         float k0[8], k1[8];
         TcOut::unpack8(c0, c1, k0);
@@ -621,9 +640,28 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   tc_fence_before();
 }
 
+// Sum COUNT per-thread floats over one particle tile (128 threads); the tile's thread 0 writes out[0..COUNT)
+// unless out is null.  scratch: 4 * COUNT floats owned by the tile.
+template <int COUNT, int NT>
+__device__ __forceinline__ void tile_sum_store(const float (&vals)[COUNT], float *scratch, float *out, int tile, int tl) {
+  const int lane = tl & 31, warp = tl >> 5;
+  if (NT == 1) __syncthreads(); else tile_sync(tile);
+#pragma unroll
+  for (int i = 0; i < COUNT; ++i) {
+    float v = vals[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) scratch[i * 4 + warp] = v;
+  }
+  if (NT == 1) __syncthreads(); else tile_sync(tile);
+  if (tl == 0 && out != nullptr) {
+    for (int i = 0; i < COUNT; ++i) out[i] = scratch[i * 4] + scratch[i * 4 + 1] + scratch[i * 4 + 2] + scratch[i * 4 + 3];
+  }
+}
+
 // =====================================================================================
-template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads, 2) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+template <int DX, int DU, int DY, int MC, int NT>
+__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -634,13 +672,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) bm_forward_tc_kernel(Dims D, Ch
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float scratch[8];
   __shared__ float vx[16];
-  TcCtx<DIN, DH, false, MC> c;
+  using Ctx = TcCtx<DIN, DH, false, MC, NT>;
+  Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
   if (threadIdx.x < DX) vx[threadIdx.x] = vxg[threadIdx.x];
   __syncthreads();
 
   const Chain ch = chains.c[blockIdx.y];
-  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const int ntiles = ceil_div(D.n_local, kTcThreads), gtile = blockIdx.x * NT + c.tile_id();
+  const int nl = gtile * kTcThreads + c.lane_id();
   const bool live = nl < D.n_local;
   const int nr = live ? nl : 0;
   const int b = (D.n_offset + nr) / D.S;
@@ -664,8 +704,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) bm_forward_tc_kernel(Dims D, Ch
 #pragma unroll
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
-    float xt[TcCtx<DIN, DH>::DINP], amax, kscale;
-    gp_forward_tc<TcCtx<DIN, DH, false, MC>, DIN, DH>(c, xin, xt, fm, fv, nullptr, amax, kscale);
+    float xt[Ctx::DINP], amax, kscale;
+    gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, nullptr, amax, kscale);
     const bool write = writer_run(t, D.R) == ch.run;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
@@ -681,11 +721,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) bm_forward_tc_kernel(Dims D, Ch
   }
   c.release();
   const float v[1] = {live ? ent : 0.f};
-  cta_sum_store<1>(v, scratch, part_out + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
+  tile_sum_store<1, NT>(v, scratch + 4 * c.tile_id(), gtile < ntiles ? part_out + ((size_t)blockIdx.y * ntiles + gtile) : nullptr,
+                        c.tile_id(), c.lane_id());
 }
 
-template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads, 2) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+template <int DX, int DU, int DY, int MC, int NT>
+__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -693,14 +734,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) fw_forward_tc_kernel(Dims D, Gp
                                                                    float *__restrict__ part_out) {
   constexpr int DH = DX - DY, DIN = DX + DU;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float scratch[4 * (DY + 1)];
+  __shared__ float scratch[NT * 4 * (DY + 1) + 8];
   __shared__ float vx[16], vy[16];
-  TcCtx<DIN, DX, false, MC> c;
+  using Ctx = TcCtx<DIN, DX, false, MC, NT>;
+  Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
   if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
   __syncthreads();
 
-  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const int ntiles = ceil_div(D.n_local, kTcThreads), gtile = blockIdx.x * NT + c.tile_id();
+  const int nl = gtile * kTcThreads + c.lane_id();
   const bool live = nl < D.n_local;
   const int nr = live ? nl : 0;
   const int b = (D.n_offset + nr) / D.S;
@@ -741,8 +784,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) fw_forward_tc_kernel(Dims D, Gp
     for (int j = 0; j < DU; ++j) xin[DX + j] = ub[t * DU + j];
     load_ytil(t + 1, yt);
     const float e = eps_f[(size_t)t * D.n_local + nr];
-    float xt[TcCtx<DIN, DX>::DINP], amax, kscale;
-    gp_forward_tc<TcCtx<DIN, DX, false, MC>, DIN, DX>(c, xin, xt, fm, fv, nullptr, amax, kscale);
+    float xt[Ctx::DINP], amax, kscale;
+    gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, nullptr, amax, kscale);
     const bool do_cond = D.condition || (t < D.R - 1);
     fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, xn, kl);
 #pragma unroll
@@ -754,7 +797,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) fw_forward_tc_kernel(Dims D, Gp
 #pragma unroll
     for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
   }
-  cta_sum_store<DY + 1>(sse, scratch, part_out + (size_t)blockIdx.x * (DY + 1));
+  tile_sum_store<DY + 1, NT>(sse, scratch + 4 * (DY + 1) * c.tile_id(), gtile < ntiles ? part_out + (size_t)gtile * (DY + 1) : nullptr,
+                             c.tile_id(), c.lane_id());
 }
 
 __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
@@ -769,8 +813,8 @@ __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
 // Reverse of the forward rollout on tcgen05: one CTA = 128 particles, T-1 steps.
 // Per-CTA output: scalar sums [L_j | sum w | sum G | var_x_bar | var_y_bar] at spart[cta].
 // =====================================================================================
-template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads, 2) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+template <int DX, int DU, int DY, int MC, int NT>
+__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -778,16 +822,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) fw_reverse_tc_kernel(Dims D, Gp
                                                                    float w_kl, Workspace ws, TcMats mats,
                                                                    float *__restrict__ spart, int nsc) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using Ctx = TcCtx<DIN, DX, true, MC>;
+  using Ctx = TcCtx<DIN, DX, true, MC, NT>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float scratch[4 * (DIN + 2 + 2 * DX)];
+  __shared__ float scratch[NT * 4 * (DIN + 2 + 2 * DX)];
   __shared__ float vx[16], vy[16];
   Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
   if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
   __syncthreads();
 
-  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const int ntiles = ceil_div(D.n_local, kTcThreads), gtile = blockIdx.x * NT + c.tile_id();
+  const int nl = gtile * kTcThreads + c.lane_id();
   const bool live = nl < D.n_local;
   const int nr = live ? nl : 0;
   const int b = (D.n_offset + nr) / D.S;
@@ -871,11 +916,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) fw_reverse_tc_kernel(Dims D, Gp
   sc[DIN] = sw; sc[DIN + 1] = sG;
 #pragma unroll
   for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = vxacc[j]; sc[DIN + 2 + DX + j] = vyacc[j]; }
-  cta_sum_store<DIN + 2 + 2 * DX>(sc, scratch, spart + (size_t)blockIdx.x * nsc);
+  tile_sum_store<DIN + 2 + 2 * DX, NT>(sc, scratch + 4 * (DIN + 2 + 2 * DX) * c.tile_id(),
+                                       gtile < ntiles ? spart + (size_t)gtile * nsc : nullptr, c.tile_id(), c.lane_id());
 }
 
-template <int DX, int DU, int DY, int MC>
-__global__ void __launch_bounds__(kTcThreads, 2) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+template <int DX, int DU, int DY, int MC, int NT>
+__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -884,9 +930,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) bm_reverse_tc_kernel(Dims D, Ch
                                                                    Workspace ws, TcMats mats,
                                                                    float *__restrict__ spart, int nsc) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using Ctx = TcCtx<DIN, DH, true, MC>;
+  using Ctx = TcCtx<DIN, DH, true, MC, NT>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float scratch[4 * (DIN + 2 + 2 * DX)];
+  __shared__ float scratch[NT * 4 * (DIN + 2 + 2 * DX)];
   __shared__ float vx[16];
   Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
@@ -894,7 +940,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) bm_reverse_tc_kernel(Dims D, Ch
   __syncthreads();
 
   const Chain ch = chains.c[blockIdx.y];
-  const int nl = blockIdx.x * kTcThreads + threadIdx.x;
+  const int ntiles = ceil_div(D.n_local, kTcThreads), gtile = blockIdx.x * NT + c.tile_id();
+  const int nl = gtile * kTcThreads + c.lane_id();
   const bool live = nl < D.n_local;
   const int nr = live ? nl : 0;
   const int b = (D.n_offset + nr) / D.S;
@@ -968,7 +1015,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) bm_reverse_tc_kernel(Dims D, Ch
   sc[DIN] = sw; sc[DIN + 1] = sG;
 #pragma unroll
   for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = (j < DH) ? vxacc[j < DH ? j : 0] : 0.f; sc[DIN + 2 + DX + j] = 0.f; }
-  cta_sum_store<DIN + 2 + 2 * DX>(sc, scratch, spart + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nsc);
+  tile_sum_store<DIN + 2 + 2 * DX, NT>(sc, scratch + 4 * (DIN + 2 + 2 * DX) * c.tile_id(),
+                                       gtile < ntiles ? spart + ((size_t)blockIdx.y * ntiles + gtile) * nsc : nullptr,
+                                       c.tile_id(), c.lane_id());
 }
 
 template <int DX, int DU, int DY>
@@ -976,68 +1025,98 @@ struct LaunchTc {
   static constexpr int DH = DX - DY, DIN = DX + DU;
   // dims with a compile-time M = 100 instantiation (run/template.py, SpringNonlinear, Sarcos shapes)
   static constexpr bool kHas100 = (DX == 4 && (DU == 1 || DU == 2)) || DX == 14;
+  // dims whose tables can push a one-tile CTA past two CTAs per SM: the two-tile kernels are compiled too
+  static constexpr bool kDual = DX >= 8;
+  static constexpr size_t kMaxDyn = 227 * 1024;
   static size_t smem_b(int M) { return TcCtx<DIN, DH>::bytes(M); }
   static size_t smem_f(int M) { return TcCtx<DIN, DX>::bytes(M); }
   static size_t smem_rb(int M) { return TcCtx<DIN, DH, true>::bytes(M); }
   static size_t smem_rf(int M) { return TcCtx<DIN, DX, true>::bytes(M); }
 
+  // Launch `k1` (one particle tile per CTA) or, when only one such CTA fits an SM and the two-tile CTA fits
+  // at all, `k2` (two tiles sharing P and the tables).  `launch(kernel, grid_x, threads, smem)` enqueues.
+  template <class K1, class K2, class F>
+  static cudaError_t pick(K1 k1, K2 k2, size_t smem1, size_t smem2, int n_local, F launch) {
+    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if (e != cudaSuccess) return e;
+    const int tiles = ceil_div(n_local, kTcThreads);
+    if constexpr (kDual) {
+      int nb = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1, kTcThreads, smem1);
+      if (e != cudaSuccess) return e;
+      if (nb < 2 && smem2 <= kMaxDyn) {
+        e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return e;
+        launch(k2, ceil_div(tiles, 2), 2 * kTcThreads, smem2);
+        return cudaGetLastError();
+      }
+    }
+    launch(k1, tiles, kTcThreads, smem1);
+    return cudaGetLastError();
+  }
+
   static cudaError_t fw_reverse(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
                                 const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
                                 TcMats mats, float *spart, int nsc, cudaStream_t st) {
-    const size_t smem = smem_rf(D.M);
-    auto go = [&](auto kernel) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      kernel<<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats,
-                                                                        spart, nsc);
-      return cudaGetLastError();
+    auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
+      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, spart, nsc);
     };
-    if constexpr (kHas100) { if (D.M == 100) return go(fw_reverse_tc_kernel<DX, DU, DY, 100>); }
-    return go(fw_reverse_tc_kernel<DX, DU, DY, 0>);
+    const size_t s1 = TcCtx<DIN, DX, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, true, 0, 2>::bytes(D.M);
+    if constexpr (kHas100) {
+      if (D.M == 100)
+        return pick(fw_reverse_tc_kernel<DX, DU, DY, 100, 1>, fw_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
+                    D.n_local, launch);
+    }
+    return pick(fw_reverse_tc_kernel<DX, DU, DY, 0, 1>, fw_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
+                launch);
   }
   static cudaError_t bm_reverse(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
                                 const float *y, const float *eps_b, const float *z_b, float w_en, Workspace ws,
                                 TcMats mats, float *spart, int nsc, cudaStream_t st) {
     if (ct.count == 0) return cudaSuccess;
-    const size_t smem = smem_rb(D.M);
-    dim3 grid(ceil_div(D.n_local, kTcThreads), ct.count);
-    auto go = [&](auto kernel) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      kernel<<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats, spart, nsc);
-      return cudaGetLastError();
+    auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
+      kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats, spart, nsc);
     };
-    if constexpr (kHas100) { if (D.M == 100) return go(bm_reverse_tc_kernel<DX, DU, DY, 100>); }
-    return go(bm_reverse_tc_kernel<DX, DU, DY, 0>);
+    const size_t s1 = TcCtx<DIN, DH, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, true, 0, 2>::bytes(D.M);
+    if constexpr (kHas100) {
+      if (D.M == 100)
+        return pick(bm_reverse_tc_kernel<DX, DU, DY, 100, 1>, bm_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
+                    D.n_local, launch);
+    }
+    return pick(bm_reverse_tc_kernel<DX, DU, DY, 0, 1>, bm_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
+                launch);
   }
 
   static cudaError_t bm_forward(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
                                 const float *y, const float *eps_b, const float *z_b, Workspace ws,
                                 float *part_out, cudaStream_t st) {
     if (ct.count == 0) return cudaSuccess;
-    const size_t smem = smem_b(D.M);
-    dim3 grid(ceil_div(D.n_local, kTcThreads), ct.count);
-    auto go = [&](auto kernel) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      kernel<<<grid, kTcThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
-      return cudaGetLastError();
+    auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
+      kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
     };
-    if constexpr (kHas100) { if (D.M == 100) return go(bm_forward_tc_kernel<DX, DU, DY, 100>); }
-    return go(bm_forward_tc_kernel<DX, DU, DY, 0>);
+    const size_t s1 = TcCtx<DIN, DH, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, false, 0, 2>::bytes(D.M);
+    if constexpr (kHas100) {
+      if (D.M == 100)
+        return pick(bm_forward_tc_kernel<DX, DU, DY, 100, 1>, bm_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
+                    D.n_local, launch);
+    }
+    return pick(bm_forward_tc_kernel<DX, DU, DY, 0, 1>, bm_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
+                launch);
   }
   static cudaError_t fw_forward(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
                                 const float *y, const float *eps_f, Workspace ws, float *part_out,
                                 cudaStream_t st) {
-    const size_t smem = smem_f(D.M);
-    auto go = [&](auto kernel) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      kernel<<<ceil_div(D.n_local, kTcThreads), kTcThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, ws, part_out);
-      return cudaGetLastError();
+    auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
+      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, ws, part_out);
     };
-    if constexpr (kHas100) { if (D.M == 100) return go(fw_forward_tc_kernel<DX, DU, DY, 100>); }
-    return go(fw_forward_tc_kernel<DX, DU, DY, 0>);
+    const size_t s1 = TcCtx<DIN, DX, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, false, 0, 2>::bytes(D.M);
+    if constexpr (kHas100) {
+      if (D.M == 100)
+        return pick(fw_forward_tc_kernel<DX, DU, DY, 100, 1>, fw_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
+                    D.n_local, launch);
+    }
+    return pick(fw_forward_tc_kernel<DX, DU, DY, 0, 1>, fw_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
+                launch);
   }
 };
 
