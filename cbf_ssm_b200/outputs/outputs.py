@@ -29,17 +29,19 @@ except ImportError:                                    # pragma: no cover
 
 class Outputs:
 
+    BEST = 'best.ckpt'
+
     def __init__(self, out_dir):
+        os.makedirs(out_dir, exist_ok=True)
         self.out_dir = out_dir
         self.ds = self.model = self.model_path = self.trainer = self.last_rmse = None
-        os.makedirs(out_dir, exist_ok=True)
 
+    # -- wiring (outputs.py:23-34) ---------------------------------------------------------
     def set_ds(self, ds):
         self.ds = ds
 
     def set_model(self, model, model_dir):
-        self.model = model
-        self.model_path = os.path.join(model_dir, 'best.ckpt')
+        self.model, self.model_path = model, os.path.join(model_dir, self.BEST)
 
     def set_trainer(self, trainer):
         self.trainer = trainer
@@ -48,91 +50,96 @@ class Outputs:
         return self.last_rmse
 
     def create_all(self):
+        """Restore the best checkpoint and write every report (outputs.py:36-49)."""
         if self.model is None or self.ds is None:
             raise AssertionError("set_model and set_ds first")
         with self.model.graph.as_default(), Session(self.model) as sess:
             self.model.saver.restore(sess, self.model_path)
             print("Generating outputs...")
-            self._create_all(sess)
+            for step in (self.training_stats, self.prediction, self.test_mse, self.var_dump):
+                step(sess)
 
-    def _create_all(self, sess):
-        self.training_stats()
-        self.prediction(sess)
-        self.test_mse(sess)
-        self.var_dump(sess)
+    def _create_all(self, sess):                       # kept for callers that hold their own session
+        for step in (self.training_stats, self.prediction, self.test_mse, self.var_dump):
+            step(sess)
 
-    def _file(self, name):
+    def _path(self, name):
         return os.path.join(self.out_dir, name)
 
-    # ---------------------------------------------------------------------------------
-    def training_stats(self):
-        if self.trainer is None:
-            return
-        print("  training stats")
-        rows = np.column_stack((np.arange(len(self.trainer.train_all)), self.trainer.train_all,
-                                self.trainer.test_all))
-        np.savetxt(self._file('training_loss.txt'), rows, header="epoch train test")
-        if plt is not None:                            # pragma: no cover
-            plt.figure(1)
-            plt.plot(self.trainer.train_all, label='train')
-            plt.plot(self.trainer.test_all, label='test')
-            plt.legend()
-            plt.savefig(self._file('training_loss.pdf'))
-            plt.close(1)
-
-    def _predict_one(self, sess, data_in, data_out):
+    def _free_run(self, sess, data_in, data_out):
+        """condition=False prediction of one window, denormalised: mean, std, ground truth [T, dy]."""
         model, ds = self.model, self.ds
         model.load_ds(sess, data_in, data_out)
         mean, var = sess.run((model.pred_mean, model.pred_var), feed_dict={model.condition: False})
-        return (ds.denormalize(mean, 'out')[0], ds.denormalize(np.sqrt(var), 'out', shift=False)[0],
-                ds.denormalize(data_out, 'out')[0])
+        to_units = lambda a, shift=True: ds.denormalize(a, 'out', shift=shift)[0]
+        return to_units(mean), to_units(np.sqrt(var), False), to_units(data_out)
+
+    # -- reports ---------------------------------------------------------------------------
+    def training_stats(self, sess=None):
+        tr = self.trainer
+        if tr is None:
+            return
+        print("  training stats")
+        table = np.stack((np.arange(len(tr.train_all), dtype=float), np.asarray(tr.train_all, dtype=float),
+                          np.asarray(tr.test_all, dtype=float)), axis=1)
+        np.savetxt(self._path('training_loss.txt'), table, header="epoch train test")
+        if plt is not None:                            # pragma: no cover
+            fig = plt.figure()
+            plt.plot(table[:, 1], label='train')
+            plt.plot(table[:, 2], label='test')
+            plt.legend()
+            fig.savefig(self._path('training_loss.pdf'))
+            plt.close(fig)
 
     def prediction(self, sess, predict_size=300):
         print("  prediction")
         ds = self.ds
-        predict_size = min(ds.train_in.shape[1], predict_size)
-        for split, din, dout in (('train', ds.train_in, ds.train_out), ('test', ds.test_in, ds.test_out)):
-            mean, std, gt = self._predict_one(sess, din[0:1, :predict_size], dout[0:1, :predict_size])
-            scipy.io.savemat(self._file('predict_%s.mat' % split), {'mean': mean, 'std': std, 'gt': gt})
+        n = min(ds.train_in.shape[1], predict_size)
+        splits = {'train': (ds.train_in, ds.train_out), 'test': (ds.test_in, ds.test_out)}
+        for name, (din, dout) in splits.items():
+            mean, std, truth = self._free_run(sess, din[:1, :n], dout[:1, :n])
+            scipy.io.savemat(self._path('predict_%s.mat' % name), {'mean': mean, 'std': std, 'gt': truth})
             if plt is not None:                        # pragma: no cover
-                steps = np.arange(mean.shape[0])
-                plt.figure(1, figsize=(6, 4))
-                plt.plot(gt[:, 0], label='ground truth')
+                fig = plt.figure(figsize=(6, 4))
+                band = 1.96 * std[:, 0]
+                plt.plot(truth[:, 0], label='ground truth')
                 plt.plot(mean[:, 0], label='prediction')
-                plt.fill_between(steps, mean[:, 0] - 1.96 * std[:, 0], mean[:, 0] + 1.96 * std[:, 0], alpha=0.4)
+                plt.fill_between(np.arange(len(band)), mean[:, 0] - band, mean[:, 0] + band, alpha=0.4)
                 plt.legend(loc=2)
                 plt.grid(True)
                 plt.xlabel("time (steps)")
-                plt.savefig(self._file('predict_%s.pdf' % split), bbox_inches='tight')
-                plt.close(1)
+                fig.savefig(self._path('predict_%s.pdf' % name), bbox_inches='tight')
+                plt.close(fig)
 
     def test_mse(self, sess):
+        """Whole test experiments, one at a time; MSE = mean over experiments of the mean squared error
+        over (time, dim) in data units (sklearn's uniform average), RMSE = sqrt of that mean."""
         print("  test mse")
         model, ds = self.model, self.ds
-        per_experiment = []
-        for i in range(ds.test_in.shape[0]):
-            model.load_ds(sess, ds.test_in[i:i + 1], ds.test_out[i:i + 1])
+        errs = []
+        for exp_in, exp_out in zip(ds.test_in, ds.test_out):
+            model.load_ds(sess, exp_in[None], exp_out[None])
             pred = model.run(sess, model.pred_mean, {model.condition: False})[0]
-            pred = ds.denormalize(pred, 'out')[0]
-            truth = ds.denormalize(ds.test_out[i:i + 1], 'out')[0]
-            per_experiment.append(float(np.mean((truth - pred) ** 2)))   # sklearn mean_squared_error: uniform average
-        mse = float(np.mean(per_experiment))
-        rmse = math.sqrt(mse)
-        with open(self._file('mse.txt'), 'w') as fh:
-            fh.write("MSE:  %f\n" % mse)
-            fh.write("RMSE: %f\n" % rmse)
-        self.last_rmse = rmse
+            diff = ds.denormalize(pred, 'out')[0] - ds.denormalize(exp_out[None], 'out')[0]
+            errs.append(float(np.mean(diff * diff)))
+        mse = float(np.mean(errs))
+        self.last_rmse = math.sqrt(mse)
+        with open(self._path('mse.txt'), 'w') as fh:
+            fh.write("MSE:  %f\nRMSE: %f\n" % (mse, self.last_rmse))
 
     def var_dump(self, sess):
+        """Every model.var_dict entry: name, then '% .4e' values (one line per matrix row), blank line."""
         print("  var dump")
-        model = self.model
-        with open(self._file('var_dump.txt'), 'w') as fh:
-            for name, handle in model.var_dict.items():
-                value = np.asarray(sess.run(handle, feed_dict={model.condition: False}))
-                fh.write(name + ":\n")
-                if value.ndim == 1:
-                    fh.write("".join("  % .4e" % v for v in value))
-                elif value.ndim == 2:
-                    for row in value:
-                        fh.write("".join("  % .4e" % v for v in row) + "\n")
-                fh.write("\n\n")
+        fmt = lambda row: "".join("  % .4e" % v for v in row)
+        chunks = []
+        for name, handle in self.model.var_dict.items():
+            value = np.asarray(sess.run(handle, feed_dict={self.model.condition: False}))
+            if value.ndim == 1:
+                body = fmt(value)
+            elif value.ndim == 2:
+                body = "".join(fmt(row) + "\n" for row in value)
+            else:
+                body = ""
+            chunks.append(name + ":\n" + body + "\n\n")
+        with open(self._path('var_dump.txt'), 'w') as fh:
+            fh.write("".join(chunks))
