@@ -51,6 +51,10 @@ CASES = [
     (8, 1, 4, 20, 7, 5, 14, 16, 2.0, (10.0, 0.0), True, True),
     (16, 1, 8, 20, 6, 3, 8, 2, 1.0, (10.0, 0.3), True, True),
     (13, 6, 7, 20, 40, 4, 12, 4, 1.0, (20.0, 0.2), True, False),
+    # D >= 8 on the tensor path: two 128-particle tiles per CTA; 3 tiles = one full CTA + one CTA whose second
+    # tile is empty and whose first is partly filled
+    (8, 1, 4, 64, 30, 11, 10, 4, 1.0, (10.0, 0.5), True, True),
+    (14, 7, 7, 50, 26, 10, 8, 3, 50.0, (6.0, 0.0), True, True),
 ]
 
 # 12 = CBF_FLAG_FORCE_REGISTER | CBF_FLAG_FORCE_TENSOR_CORES: the register-resident kernels
