@@ -149,7 +149,7 @@ struct TcCtx {
   static size_t bytes(int M) {
     const int MP = round_up(M, 16);
     return (size_t)2 * MP * MP * 2 + (size_t)NT * 2 * kTcThreads * MP * 2 +
-           sizeof(float) * ((size_t)M * (DINP + 2 * DOUTP) + DINP + 4) + 64;
+           sizeof(float) * ((size_t)MP * (DINP + 2 * DOUTP) + DINP + 4) + 64;
   }
 
   // Carve + fill (all threads).  Allocates TMEM (warp 0) and initialises the mbarrier.
@@ -165,9 +165,12 @@ struct TcCtx {
     // The reverse pass reuses the K operand buffers for b (k is re-read from the float32 operand
     // matrix it was just written to, an L2 hit), which keeps the CTA at ~114 KB: two CTAs per SM.
     B1 = K1; B2 = K2;
-    float *Zw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DINP;
-    float *aw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
-    float *Sw = reinterpret_cast<float *>(base); base += sizeof(float) * M * DOUTP;
+    // The tables have MP rows: rows >= M hold Z/ell = 1e18 (squared distance ~1e37, so k'' underflows to an
+    // exact 0 and never wins the minimum) and alpha = S = 0, which makes every padded row contribute exact
+    // zeros everywhere -- the per-row loops need no m < M guards.
+    float *Zw = reinterpret_cast<float *>(base); base += sizeof(float) * MP * DINP;
+    float *aw = reinterpret_cast<float *>(base); base += sizeof(float) * MP * DOUTP;
+    float *Sw = reinterpret_cast<float *>(base); base += sizeof(float) * MP * DOUTP;
     float *iw = reinterpret_cast<float *>(base); base += sizeof(float) * (DINP + 4);
     uint64_t *barp = reinterpret_cast<uint64_t *>(base); base += 32;   // one mbarrier per tile
     uint32_t *tmemp = reinterpret_cast<uint32_t *>(base); base += 16;
@@ -195,14 +198,15 @@ struct TcCtx {
       P1[i] = h1;
       P2[i] = h2;
     }
-    for (int i = tid; i < M * DINP; i += nt) {
+    for (int i = tid; i < MP * DINP; i += nt) {
       const int r = i / DINP, c = i % DINP;
-      Zw[i] = (c < DIN) ? g.Z[r * DIN + c] / g.ell[c] : 0.f;
+      Zw[i] = (c < DIN) ? (r < M ? g.Z[r * DIN + c] / g.ell[c] : 1e18f) : 0.f;
     }
-    for (int i = tid; i < M * DOUTP; i += nt) {
+    for (int i = tid; i < MP * DOUTP; i += nt) {
       const int r = i / DOUTP, c = i % DOUTP;
-      aw[i] = (c < DOUT) ? g.alpha[r * DOUT + c] : 0.f;
-      Sw[i] = (c < DOUT) ? g.S[r * DOUT + c] : 0.f;
+      const bool ok = (c < DOUT && r < M);
+      aw[i] = ok ? g.alpha[r * DOUT + c] : 0.f;
+      Sw[i] = ok ? g.S[r * DOUT + c] : 0.f;
     }
     for (int i = tid; i < DINP; i += nt) iw[i] = (i < DIN) ? 1.f / g.ell[i] : 0.f;
     Zt = Zw; al = aw; Sm = Sw; il = iw;
@@ -291,11 +295,17 @@ __device__ __forceinline__ void tc_read_row16(const __half *b1, const __half *b2
   }
 }
 __device__ __forceinline__ void tc_write_row8(__half *b1, __half *b2, int row, int ch, const float (&v)[8]) {
-  __half h1[8], h2[8];
+  uint32_t w1[4], w2[4];   // two values per conversion (F2FP) instead of one (F2F)
 #pragma unroll
-  for (int e = 0; e < 8; ++e) split_h(v[e], h1[e], h2[e]);
-  const uint4 v1 = make_uint4(pack_h2(h1[0], h1[1]), pack_h2(h1[2], h1[3]), pack_h2(h1[4], h1[5]), pack_h2(h1[6], h1[7]));
-  const uint4 v2 = make_uint4(pack_h2(h2[0], h2[1]), pack_h2(h2[2], h2[3]), pack_h2(h2[4], h2[5]), pack_h2(h2[6], h2[7]));
+  for (int e = 0; e < 4; ++e) {
+    const __half2 h1 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    const float2 f1 = __half22float2(h1);
+    const __half2 h2 = __floats2half2_rn(v[2 * e] - f1.x, v[2 * e + 1] - f1.y);
+    w1[e] = *reinterpret_cast<const uint32_t *>(&h1);
+    w2[e] = *reinterpret_cast<const uint32_t *>(&h2);
+  }
+  const uint4 v1 = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+  const uint4 v2 = make_uint4(w2[0], w2[1], w2[2], w2[3]);
   const size_t off = (size_t)ch * (kTcThreads * 8) + row * 8;
   *reinterpret_cast<uint4 *>(b1 + off) = v1;
   *reinterpret_cast<uint4 *>(b2 + off) = v2;
@@ -403,15 +413,12 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int m = ch * 8 + e;
-      float d2 = 3.0e38f;
-      if (m < M) {
-        float z[DINP];
-        ld_row<DINP>(c.Zt + m * DINP, z);
-        d2 = 0.f;
+      float z[DINP];
+      ld_row<DINP>(c.Zt + m * DINP, z);
+      float d2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < DIN; ++j) { const float dl = xt[j] - z[j]; d2 = fmaf(dl, dl, d2); }
-        d2min = fminf(d2min, d2);
-      }
+      for (int j = 0; j < DIN; ++j) { const float dl = xt[j] - z[j]; d2 = fmaf(dl, dl, d2); }
+      d2min = fminf(d2min, d2);
       dv[e] = d2;
     }
     const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
@@ -428,14 +435,11 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int m = ch * 8 + e;
-      float kp = 0.f;
-      if (m < M) {
-        kp = fast_exp2(kNegHalfLog2e * (dv[e] - d2min));
-        float al[DOUTP];
-        ld_row<DOUTP>(c.al + m * DOUTP, al);
+      const float kp = fast_exp2(kNegHalfLog2e * (dv[e] - d2min));
+      float al[DOUTP];
+      ld_row<DOUTP>(c.al + m * DOUTP, al);
 #pragma unroll
-        for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(kp, al[d], fm[d]);
-      }
+      for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(kp, al[d], fm[d]);
       kv[e] = kp;
     }
     tc_write_row8(c.K1, c.K2, t, ch, kv);
@@ -467,15 +471,13 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
-      if (m < M) {
-        q = fmaf(kp[e], a[e], q);
-        amax = fmaxf(amax, fabsf(a[e]));
-        const float a2 = a[e] * a[e];
-        float S[DOUTP];
-        ld_row<DOUTP>(c.Sm + m * DOUTP, S);
+      q = fmaf(kp[e], a[e], q);
+      amax = fmaxf(amax, fabsf(a[e]));
+      const float a2 = a[e] * a[e];
+      float S[DOUTP];
+      ld_row<DOUTP>(c.Sm + m * DOUTP, S);
 #pragma unroll
-        for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, S[d], fv[d]);
-      }
+      for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, S[d], fv[d]);
     }
   }
   // q, fv, amax were formed from the normalised k'' and a'' = P' k''; undo the per-particle scale
@@ -532,19 +534,14 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
-      float b = 0.f, asq = 0.f;
-      if (m < M) {
-        float S[DOUTP];
-        ld_row<DOUTP>(c.Sm + m * DOUTP, S);
-        float cm = 0.f;
+      float S[DOUTP];
+      ld_row<DOUTP>(c.Sm + m * DOUTP, S);
+      float cm = 0.f;
 #pragma unroll
-        for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], gv[d], cm);
-        b = a[e] * cm * bsc;
-        const float at = ascale * a[e];
-        asq = at * at;
-      }
-      bv[e] = b;
-      a2[e] = asq;
+      for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], gv[d], cm);
+      const float at = ascale * a[e];
+      bv[e] = a[e] * cm * bsc;
+      a2[e] = at * at;
     }
     float lo[8], hi[8];
 #pragma unroll
@@ -594,30 +591,25 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
-      if (m < M) {
-        float al[DOUTP];
-        ld_row<DOUTP>(c.al + m * DOUTP, al);
-        float kb = 2.f * pbs * pb[e] - 2.f * Gs * ascale * a[e];
+      float al[DOUTP];
+      ld_row<DOUTP>(c.al + m * DOUTP, al);
+      float kb = 2.f * pbs * pb[e] - 2.f * Gs * ascale * a[e];
 #pragma unroll
-        for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gm[d], kb);
-        const float k = sig2 * kp[e];
-        const float w = kb * k;
-        sw += w;
-        float z[DINP];
-        ld_row<DINP>(c.Zt + m * DINP, z);
+      for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gm[d], kb);
+      const float k = sig2 * kp[e];
+      const float w = kb * k;
+      sw += w;
+      float z[DINP];
+      ld_row<DINP>(c.Zt + m * DINP, z);
 #pragma unroll
-        for (int j = 0; j < DIN; ++j) {
-          const float dl = xt[j] - z[j];
-          const float wd = w * dl;
-          if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
-          Lacc[j] = fmaf(wd, dl, Lacc[j]);
-        }
-        wv[e] = w;
-        abv[e] = 2.f * bs * bb[e] - Gs * k;
-      } else {
-        wv[e] = 0.f;
-        abv[e] = 0.f;
+      for (int j = 0; j < DIN; ++j) {
+        const float dl = xt[j] - z[j];
+        const float wd = w * dl;
+        if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
+        Lacc[j] = fmaf(wd, dl, Lacc[j]);
       }
+      wv[e] = w;
+      abv[e] = 2.f * bs * bb[e] - Gs * k;
     }
     if (live) {
       float lo[8], hi[8];
