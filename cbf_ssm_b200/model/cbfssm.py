@@ -134,12 +134,21 @@ class CBFSSM(BaseModel):
                             else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)))
         u, y = as_f32(u_host), as_f32(y_host)      # pinned tensors are copied asynchronously
         B, T, _ = u.shape
-        ud = u.to(dev, non_blocking=True)
-        yd = y.to(dev, non_blocking=True)
+        # host -> device copies go on a side stream and overlap the generation of the step's normal draws
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        self._copy_stream.wait_stream(main)
+        with torch.cuda.stream(self._copy_stream):
+            ud = u.to(dev, non_blocking=True)
+            yd = y.to(dev, non_blocking=True)
         n0, nl = self._shard(B)
         if nl < 1:
             raise ValueError("minibatch has fewer particles than ranks")
         eb, zb, ef = self._draws(B, T, n0, nl)
+        main.wait_stream(self._copy_stream)
+        ud.record_stream(main)
+        yd.record_stream(main)
         out = eng.forward(ud, yd, eb, zb, ef, condition=condition, n_offset=n0, n_local=nl)
         if "train" in names:
             eng.backward()                   # all-reduces gradient + terms when sharded
