@@ -290,7 +290,8 @@ def run_b200(args):
     # algorithmic FLOPs per particle-step attributed to each kernel (1 gp_f + 2 gp_b evaluations)
     kflops = [2 * bf, ff, fb, 2 * bb]
     knames = ["bm_forward", "fw_forward", "fw_reverse", "bm_reverse"]
-    kavg = [kms[i] / max(kcnt[i], 1) for i in range(4)]
+    # kernel time per step (a kernel may be launched several times per step: chain batches, time windows)
+    kavg = [kms[i] / args.steps for i in range(4)]
     dom = int(np.argmax([kms[i] for i in range(4)]))
     simt_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12     # TFLOP/s
     achieved = kflops[dom] * psteps_local / (kavg[dom] * 1e-3) / 1e12
@@ -311,9 +312,8 @@ def run_b200(args):
                                "compute-bound (SURVEY 8d), not HBM- or tensor-bound",
                 "flops_per_particle_step": {k: v for k, v in zip(knames, kflops)},
                 "kernel_ms_avg": {**{k: v for k, v in zip(knames, kavg)},
-                                  **({"outer_f": kms[4] / kcnt[4], "outer_b": kms[5] / kcnt[5]} if kcnt[4] else {})},
-                "kernel_share_of_step": {k: (kms[i] / max(kcnt[i], 1)) * (kcnt[i] / args.steps) / ms_per_step
-                                         for i, k in enumerate(knames)},
+                                  **({"outer_f": kms[4] / args.steps, "outer_b": kms[5] / args.steps} if kcnt[4] else {})},
+                "kernel_share_of_step": {k: kavg[i] / ms_per_step for i, k in enumerate(knames)},
                 "whole_step_frac": step_frac,
                 **({"note": "tensor path: the M^2 contractions run on tcgen05 (fp16/bf16 splits, 3 MMA passes), so "
                             "algorithmic FLOPs against the FP32-SIMT peak can exceed 1; the kernels are bound by the "

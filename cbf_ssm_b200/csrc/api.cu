@@ -1,6 +1,7 @@
 // C ABI of cbfssm_b200 (see include/cbfssm_b200.h): shape checks, workspace layout,
 // chain schedule, kernel dispatch and the small float64 reduction kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -91,11 +92,12 @@ static std::vector<Chain> build_chains(int T, int R) {
       for (int t = t_hi; t > t_next; --t)
         if (writer_run(t, R) == run) t_lo = t;
       if (t_lo < 0) continue;   // segment writes nothing: dead work
-      out.push_back(Chain{run, t_hi, t_lo, resample ? 1 : 0, 0});
+      out.push_back(Chain{run, t_hi, t_lo, resample ? 1 : 0, 0, t_hi, 0, 0});
     }
   }
   int col = 0;
   for (Chain &c : out) { c.col0 = col; col += c.t_hi - c.t_lo + 1; }
+  for (size_t i = 0; i < out.size(); ++i) out[i].id = (int)i;
   return out;
 }
 
@@ -114,10 +116,24 @@ struct Plan {
   size_t colsf, colsb;           // columns (live steps x particles) of the operand matrices
   size_t off_rpart;              // per-CTA float64 partials of the tcgen05 outer-product kernel
   int ctot_f, ctot_b, nsc_f, nsc_b, nspart_f, nspart_b;
-  size_t off_mf, off_mb, off_spf, off_spb, off_rdf, off_rdb;
+  size_t off_mats, off_spf, off_spb, off_rdf, off_rdb, off_carry_f, off_carry_b;
+  // time windows of the tensor-path reverse pass (the operand tiles of one window fit the window budget)
+  std::vector<TimeWin> win_f;                 // forward-rollout reverse: descending time
+  std::vector<std::vector<Chain>> rounds_b;   // message reverse: r-th piece of every chain, ascending time
 };
 
-constexpr size_t kTcMaxMatBytes = (size_t)64 << 30;
+// Budget for the outer-product operand tiles of one time window of the tensor-path reverse pass (one buffer,
+// used by the forward-rollout GP's windows and then by the message GP's).  Calls whose tiles fit run as one
+// window; CBFSSM_B200_TC_WINDOW_BYTES overrides it (the tests use it to force many windows).
+constexpr size_t kTcWindowBytes = (size_t)40 << 30;
+static size_t tc_window_budget() {
+  const char *e = getenv("CBFSSM_B200_TC_WINDOW_BYTES");
+  if (e != nullptr && *e) {
+    const long long v = atoll(e);
+    if (v > 0) return (size_t)v;
+  }
+  return kTcWindowBytes;
+}
 constexpr int kOuterMaxGrid = 148 * 2;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -200,24 +216,61 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
     p.colsb = (size_t)live * s->n_local;
     p.ctot_f = s->M + 2 * p.dx + p.din + 1;
     p.ctot_b = s->M + 2 * p.dh + p.din + 1;
-    const size_t bytes_f = mats_bytes(p.colsf, s->M, p.dx, p.din), bytes_b = mats_bytes(p.colsb, s->M, p.dh, p.din);
-    const size_t bytes = bytes_f + bytes_b;
     p.tc_rev = p.tc_fwd && p.ops->fw_reverse_tc != nullptr && p.ops->smem_tc(s->M, 2) <= kMaxSmem &&
-               p.ops->smem_tc(s->M, 3) <= kMaxSmem && bytes <= kTcMaxMatBytes && p.colsf > 0 && (p.colsb > 0 || p.half) &&
-               p.colsf < ((size_t)1 << 31) && p.colsb < ((size_t)1 << 31);
+               p.ops->smem_tc(s->M, 3) <= kMaxSmem && p.colsf > 0 && (p.colsb > 0 || p.half);
     if (p.tc_rev) {
+      // ---- time windows ----
+      const size_t budget = tc_window_budget();
+      const size_t col_f = mats_bytes(kOT, s->M, p.dx, p.din) / kOT, col_b = mats_bytes(kOT, s->M, p.dh, p.din) / kOT;
+      const int steps_f = s->T - 1;
+      size_t wmax = budget / (col_f * (size_t)s->n_local);
+      if (wmax < 1) wmax = 1;
+      if (wmax * (size_t)s->n_local >= ((size_t)1 << 31)) wmax = (((size_t)1 << 31) - 1) / s->n_local;
+      const int nwin_f = (int)((steps_f + wmax - 1) / wmax), wf = ceil_div(steps_f, nwin_f);
+      p.win_f.clear();
+      for (int hi = steps_f - 1; hi >= 0; hi -= wf) {
+        const int lo = hi - wf + 1 > 0 ? hi - wf + 1 : 0;
+        p.win_f.push_back(TimeWin{hi, lo, hi == steps_f - 1 ? 1 : 0, lo == 0 ? 1 : 0});
+      }
+      size_t bytes_win = mats_bytes((size_t)wf * s->n_local, s->M, p.dx, p.din);
+      p.rounds_b.clear();
+      if (!p.half) {
+        const size_t nchains = p.chains.size();
+        size_t wb = budget / (col_b * (size_t)s->n_local * nchains);
+        if (wb < 1) wb = 1;
+        if (wb * nchains * (size_t)s->n_local >= ((size_t)1 << 31)) wb = (((size_t)1 << 31) - 1) / ((size_t)s->n_local * nchains);
+        if (wb < 1) { set_error("too many particles for one time step of operand tiles"); return CBF_ERR_INVALID_SHAPE; }
+        for (const Chain &c : p.chains) {
+          const int len = c.t_hi - c.t_lo + 1, npieces = (int)((len + wb - 1) / wb), plen = ceil_div(len, npieces);
+          for (int k = 0; k < npieces; ++k) {
+            Chain piece = c;
+            piece.t_lo = c.t_lo + k * plen;
+            piece.t_hi = piece.t_lo + plen - 1 < c.t_hi ? piece.t_lo + plen - 1 : c.t_hi;
+            piece.carry = (k > 0 ? 1 : 0) | (k + 1 < npieces ? 2 : 0);
+            if ((int)p.rounds_b.size() <= k) p.rounds_b.emplace_back();
+            p.rounds_b[k].push_back(piece);
+          }
+        }
+        for (auto &round : p.rounds_b) {
+          int col = 0;
+          for (Chain &c : round) { c.col0 = col; col += c.t_hi - c.t_lo + 1; }
+          const size_t b = mats_bytes((size_t)col * s->n_local, s->M, p.dh, p.din);
+          if (b > bytes_win) bytes_win = b;
+        }
+      }
       p.nsc_f = p.Lf.slot() - p.Lf.scal_off();
       p.nsc_b = p.Lb.slot() - p.Lb.scal_off();
       const int pt = ceil_div(s->n_local, 128);
       p.nspart_f = pt;
       p.nspart_b = pt * (int)p.chains.size();
-      p.off_mf = o; o = align_up(o + bytes_f, 256);
-      p.off_mb = o; o = align_up(o + bytes_b, 256);
+      p.off_mats = o; o = align_up(o + bytes_win, 256);
       p.off_rpart = o; o = align_up(o + sizeof(double) * (size_t)kOuterMaxGrid * 128 * kOCols, 256);
       p.off_spf = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_f * p.nsc_f, 256);
       p.off_spb = o; o = align_up(o + sizeof(float) * (size_t)p.nspart_b * p.nsc_b, 256);
       p.off_rdf = o; o = align_up(o + sizeof(double) * (size_t)s->M * p.ctot_f, 256);
       p.off_rdb = o; o = align_up(o + sizeof(double) * (size_t)s->M * p.ctot_b, 256);
+      p.off_carry_f = o; o = align_up(o + sizeof(float) * p.dx * np, 256);
+      p.off_carry_b = o; o = align_up(o + sizeof(float) * (p.chains.size() + 1) * p.dh * np, 256);
     }
   }
   p.total = o;
@@ -245,7 +298,8 @@ static cudaError_t clear_mats_tail(const TcMats &m, cudaStream_t st) {
 }
 
 // P_bar', alpha_bar', S_bar, [U|r] of one GP on the tensor cores (kernels_outer.cuh) -> Rd [M x Ctot] float64.
-static cudaError_t tc_outer(const TcMats &m, int M, int dout, int din, double *rpart, double *Rd, cudaStream_t st) {
+static cudaError_t tc_outer(const TcMats &m, int M, int dout, int din, double *rpart, double *Rd, bool accumulate,
+                            cudaStream_t st) {
   OuterArgs a{m, M, dout, din};
   const size_t ntile = (m.L + kOT - 1) / kOT;
   int grid = device_sms();          // one CTA per SM: the 3-stage ring takes ~216 KB of shared memory
@@ -256,7 +310,7 @@ static cudaError_t tc_outer(const TcMats &m, int M, int dout, int din, double *r
   if (e != cudaSuccess) return e;
   tc_outer_kernel<<<grid, kOThreads, smem, st>>>(a, rpart);
   const int Ctot = M + 2 * dout + din + 1;
-  outer_reduce_kernel<<<ceil_div(M * Ctot, 256), 256, 0, st>>>(rpart, grid, M, dout, din, Rd);
+  outer_reduce_kernel<<<ceil_div(M * Ctot, 256), 256, 0, st>>>(rpart, grid, M, dout, din, Rd, accumulate ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -274,6 +328,8 @@ static Workspace bind_workspace(const Plan &p, void *base) {
   w.acc_b = reinterpret_cast<double *>(b + p.off_accb);
   w.stats = reinterpret_cast<double *>(b + p.off_stats);
   w.cpack = reinterpret_cast<float *>(b + p.off_cpack);
+  w.carry_f = p.tc_rev ? reinterpret_cast<float *>(b + p.off_carry_f) : nullptr;
+  w.carry_b = p.tc_rev ? reinterpret_cast<float *>(b + p.off_carry_b) : nullptr;
   w.x0 = nullptr;
   w.x0b = reinterpret_cast<float *>(b + p.off_x0b);
   w.npad = p.D.npad;
@@ -341,12 +397,13 @@ __global__ void finalize_terms_kernel(const float *__restrict__ fbm, int nbm, co
   }
 }
 
-__global__ void reduce_slots_kernel(const float *__restrict__ part, int nslots, int slot, double *__restrict__ out) {
+__global__ void reduce_slots_kernel(const float *__restrict__ part, int nslots, int slot, double *__restrict__ out,
+                                    int accumulate = 0) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= slot) return;
   double s = 0.0;
   for (int i = 0; i < nslots; ++i) s += (double)part[(size_t)i * slot + e];
-  out[e] = s;
+  out[e] = accumulate ? out[e] + s : s;
 }
 
 // Decode one GP's reduced accumulators into the flat kernel-level gradient.
@@ -694,36 +751,48 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
   if (p.tc_rev) {
     // ---- tensor-core path: rollout adjoints on tcgen05, parameter outer products as a tcgen05 split-K stream ----
     char *wb = static_cast<char *>(workspace);
-    const TcMats mf = bind_mats(workspace, p.off_mf, p.colsf, p.D.M, p.dx, p.din);
-    const TcMats mb = bind_mats(workspace, p.off_mb, p.colsb, p.D.M, p.dh, p.din);
     float *spf = reinterpret_cast<float *>(wb + p.off_spf), *spb = reinterpret_cast<float *>(wb + p.off_spb);
     double *rdf = reinterpret_cast<double *>(wb + p.off_rdf), *rdb = reinterpret_cast<double *>(wb + p.off_rdb);
-    CBF_CUDA(clear_mats_tail(mf, st));
-    if (!p.half) CBF_CUDA(clear_mats_tail(mb, st));
-    {
-      ScopedTiming tm(2, st);
-      CBF_CUDA(p.ops->fw_reverse_tc(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, mf, spf, p.nsc_f, st));
-    }
-    const int pt = ceil_div(p.D.n_local, 128);
-    for (int c0 = 0; c0 < nch; c0 += kMaxChains) {
-      ChainTable ct;
-      ct.count = nch - c0 < kMaxChains ? nch - c0 : kMaxChains;
-      memcpy(ct.c, p.chains.data() + c0, sizeof(Chain) * ct.count);
-      ScopedTiming tm(3, st);
-      CBF_CUDA(p.ops->bm_reverse_tc(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, w_en, ws, mb,
-                                    spb + (size_t)c0 * pt * p.nsc_b, p.nsc_b, st));
-    }
-    reduce_slots_kernel<<<ceil_div(p.nsc_f, 256), 256, 0, st>>>(spf, p.nspart_f, p.nsc_f, ws.acc_f + p.Lf.scal_off());
-    reduce_slots_kernel<<<ceil_div(p.nsc_b, 256), 256, 0, st>>>(spb, p.nspart_b, p.nsc_b, ws.acc_b + p.Lb.scal_off());
-    CBF_CUDA(cudaGetLastError());
     double *rpart = reinterpret_cast<double *>(wb + p.off_rpart);
-    {
+    const int pt = ceil_div(p.D.n_local, 128);
+    // forward-rollout GP: time windows from T-2 down to 0; each window's operand tiles are accumulated before
+    // the next window overwrites them (one window when everything fits the budget)
+    for (size_t wi = 0; wi < p.win_f.size(); ++wi) {
+      const TimeWin win = p.win_f[wi];
+      const TcMats mf = bind_mats(workspace, p.off_mats, (size_t)(win.t_hi - win.t_lo + 1) * p.D.n_local, p.D.M, p.dx, p.din);
+      CBF_CUDA(clear_mats_tail(mf, st));
+      {
+        ScopedTiming tm(2, st);
+        CBF_CUDA(p.ops->fw_reverse_tc(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, mf, win, spf, p.nsc_f, st));
+      }
+      reduce_slots_kernel<<<ceil_div(p.nsc_f, 256), 256, 0, st>>>(spf, p.nspart_f, p.nsc_f, ws.acc_f + p.Lf.scal_off(),
+                                                                  wi > 0 ? 1 : 0);
+      CBF_CUDA(cudaGetLastError());
       ScopedTiming tm(4, st);
-      CBF_CUDA(tc_outer(mf, p.D.M, p.dx, p.din, rpart, rdf, st));
+      CBF_CUDA(tc_outer(mf, p.D.M, p.dx, p.din, rpart, rdf, wi > 0, st));
     }
-    if (!p.half) {
+    // message GP: round r runs the r-th piece of every live chain (ascending time; the message adjoint crosses
+    // pieces through the carry buffer)
+    for (size_t ri = 0; ri < p.rounds_b.size(); ++ri) {
+      const std::vector<Chain> &round = p.rounds_b[ri];
+      int cols = 0;
+      for (const Chain &c : round) cols += c.t_hi - c.t_lo + 1;
+      const TcMats mb = bind_mats(workspace, p.off_mats, (size_t)cols * p.D.n_local, p.D.M, p.dh, p.din);
+      CBF_CUDA(clear_mats_tail(mb, st));
+      const int nr = (int)round.size();
+      for (int c0 = 0; c0 < nr; c0 += kMaxChains) {
+        ChainTable ct;
+        ct.count = nr - c0 < kMaxChains ? nr - c0 : kMaxChains;
+        memcpy(ct.c, round.data() + c0, sizeof(Chain) * ct.count);
+        ScopedTiming tm(3, st);
+        CBF_CUDA(p.ops->bm_reverse_tc(p.D, ct, to_dev(gp_b), var_x, u, y, eps_b, z_b, w_en, ws, mb,
+                                      spb + (size_t)c0 * pt * p.nsc_b, p.nsc_b, st));
+      }
+      reduce_slots_kernel<<<ceil_div(p.nsc_b, 256), 256, 0, st>>>(spb, pt * nr, p.nsc_b, ws.acc_b + p.Lb.scal_off(),
+                                                                  ri > 0 ? 1 : 0);
+      CBF_CUDA(cudaGetLastError());
       ScopedTiming tm(5, st);
-      CBF_CUDA(tc_outer(mb, p.D.M, p.dh, p.din, rpart, rdb, st));
+      CBF_CUDA(tc_outer(mb, p.D.M, p.dh, p.din, rpart, rdb, ri > 0, st));
     }
     finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dx, p.ctot_f, rdf, ws.acc_f + p.Lf.scal_off(), to_dev(gp_f),
                                                grad_flat + gl.f_P, grad_flat + gl.f_alpha, grad_flat + gl.f_S,

@@ -21,12 +21,23 @@ struct Chain {
   int run;
   int t_hi;
   int t_lo;
-  int init;  // 0: h = 0 (cbfssm.py:106)   1: h = tile(z_b[run, t_hi]) (cbfssm.py:133-135)
+  int init;  // 0: h = 0 (cbfssm.py:106)   1: h = tile(z_b[run, t_top]) (cbfssm.py:133-135)
   int col0;  // number of live steps of all earlier chains (column block of the tensor-path operand matrices)
+  // Tensor-path reverse pass in time windows: a chain may be cut into pieces [t_lo, t_hi] processed in
+  // successive launches; t_top is the whole chain's first step (where `init` applies), `carry` says whether
+  // the piece loads (bit 0) / stores (bit 1) the message adjoint in slot `id` of the carry buffer.
+  int t_top, carry, id;
 };
 struct ChainTable {
   int count;
   Chain c[kMaxChains];
+};
+
+// Time window of the tensor-path reverse of the forward rollout: steps t_hi .. t_lo (descending) in one
+// launch; `first` = the window starts at T-2 (adjoint initialised from the likelihood), `last` = it ends at
+// t = 0; otherwise the state adjoint enters / leaves through Workspace::carry_f.
+struct TimeWin {
+  int t_hi, t_lo, first, last;
 };
 
 struct GpDev {
@@ -65,6 +76,8 @@ struct Workspace {
   double *acc_f;   // [slot_f]           reduced
   double *acc_b;   // [slot_b]
   double *stats;   // sse[dy], kl_x, entropy of this shard (float64)
+  float *carry_f;  // [dx][npad]            state adjoint between time windows (tensor path)
+  float *carry_b;  // [chains][dh][npad]    message adjoint between chain pieces (tensor path)
   float *cpack;    // [2][2048] packed constant-bank images of the two GPs (register path)
   const float *x0; // CBFSSMHALF: x_0 per sequence [B][dx] (output of the recognition model)
   float *x0b;      // CBFSSMHALF: adjoint of x_0 per particle [dx][npad]
@@ -137,7 +150,7 @@ struct DimOps {
                                const float *y, const float *eps_f, Workspace, float *part_out, cudaStream_t);
   cudaError_t (*fw_reverse_tc)(const Dims &, GpDev, const float *vx, const float *vy, const float *u,
                                const float *y, const float *eps_f, float w_ll, float w_kl, Workspace, TcMats,
-                               float *spart, int nsc, cudaStream_t);
+                               TimeWin, float *spart, int nsc, cudaStream_t);
   cudaError_t (*bm_reverse_tc)(const Dims &, const ChainTable &, GpDev, const float *vx, const float *u,
                                const float *y, const float *eps_b, const float *z_b, float w_en, Workspace,
                                TcMats, float *spart, int nsc, cudaStream_t);

@@ -219,10 +219,10 @@ __global__ void __launch_bounds__(kOThreads) tc_outer_kernel(OuterArgs a, double
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-// R[m][c] (float64, [M][Ctot]) = sum over CTAs of the partials, with the TMEM column blocks mapped to
+// R[m][c] (float64, [M][Ctot]) (+)= sum over CTAs of the partials, with the TMEM column blocks mapped to
 // [P_bar' (M) | alpha_bar' (dout) | S_bar (dout) | U, r (din+1)].
 __global__ void outer_reduce_kernel(const double *__restrict__ Rpart, int nparts, int M, int dout, int din,
-                                    double *__restrict__ R) {
+                                    double *__restrict__ R, int accumulate) {
   const int Ctot = M + 2 * dout + din + 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * Ctot) return;
@@ -234,7 +234,7 @@ __global__ void outer_reduce_kernel(const double *__restrict__ Rpart, int nparts
   else src = 160 + (c - M - 2 * dout);
   double s = 0.0;
   for (int p = 0; p < nparts; ++p) s += Rpart[((size_t)p * 128 + m) * kOCols + src];
-  R[i] = s;
+  R[i] = accumulate ? R[i] + s : s;   // later time windows add to the first one's result
 }
 
 inline size_t outer_smem_bytes(int din) { return (size_t)kOStages * outer_stage_blocks(din) * kOBlk; }

@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
                                                                    const float *__restrict__ y,
                                                                    const float *__restrict__ eps_f, float w_ll,
                                                                    float w_kl, Workspace ws, TcMats mats,
-                                                                   float *__restrict__ spart, int nsc) {
+                                                                   TimeWin win, float *__restrict__ spart, int nsc) {
   constexpr int DH = DX - DY, DIN = DX + DU;
   using Ctx = TcCtx<DIN, DX, true, MC, NT>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -839,24 +839,27 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
   for (int j = 0; j < DX; ++j) { vxacc[j] = 0.f; vyacc[j] = 0.f; }
 
   float xb[DX];
-  {
+  if (win.first) {
     const float *Xp = ws.X + ((size_t)(D.T - 1) * DX) * np + nr;
 #pragma unroll
     for (int j = 0; j < DX; ++j)
       xb[j] = (j < DY && live) ? w_ll * (yb[(D.T - 1) * DY + (j < DY ? j : 0)] - Xp[j * np]) / vy[j] : 0.f;
+  } else {   // adjoint of x_{t_hi+1} left by the previous (later-in-time) window
+#pragma unroll
+    for (int j = 0; j < DX; ++j) xb[j] = live ? ws.carry_f[j * np + nr] : 0.f;
   }
   float xnext[DX];   // x_t of the coming iteration, fetched one step ahead (it heads the step's dependency chain)
   {
-    const float *Xp = ws.X + ((size_t)(D.T > 1 ? D.T - 2 : 0) * DX) * np + nr;
+    const float *Xp = ws.X + ((size_t)win.t_hi * DX) * np + nr;
 #pragma unroll
     for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
   }
 #pragma unroll 1
-  for (int t = D.T - 2; t >= 0; --t) {
+  for (int t = win.t_hi; t >= win.t_lo; --t) {
     float x[DX], xin[DIN], xt[Ctx::DINP], fm[DX], fv[DX], yt[DX], amax, kscale;
 #pragma unroll
     for (int j = 0; j < DX; ++j) { x[j] = xnext[j]; xin[j] = x[j]; }
-    if (t > 0) {
+    if (t > win.t_lo) {
       const float *Xp = ws.X + ((size_t)(t - 1) * DX) * np + nr;
 #pragma unroll
       for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
@@ -871,7 +874,7 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
       for (int j = 0; j < DH; ++j) yt[DY + j] = D.half ? 0.f : Hp[j * np];
     }
     const float e = eps_f[(size_t)t * D.n_local + nr];
-    const TcOut o = tc_out_at(mats, (size_t)t * D.n_local + nr);
+    const TcOut o = tc_out_at(mats, (size_t)(t - win.t_lo) * D.n_local + nr);
     gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale);
     const bool do_cond = D.condition || (t < D.R - 1);
     float fmb[DX], fvb[DX], ytb[DX];
@@ -893,7 +896,12 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
       xb[j] = xinb[j] + fmb[j] + lg;
     }
   }
-  if (live && D.half) {   // CBFSSMHALF: adjoint of the recognition model's x_0 (all dims)
+  if (!win.last) {
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < DX; ++j) ws.carry_f[j * np + nl] = xb[j];
+    }
+  } else if (live && D.half) {   // CBFSSMHALF: adjoint of the recognition model's x_0 (all dims)
 #pragma unroll
     for (int j = 0; j < DX; ++j) ws.x0b[j * np + nl] = xb[j];
   } else if (live) {
@@ -949,10 +957,10 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_reverse_t
 
   float hb[DH];
 #pragma unroll
-  for (int j = 0; j < DH; ++j) hb[j] = 0.f;
-  // the message state entering step t: the chain's initial value at t_hi, else the output of step t+1
+  for (int j = 0; j < DH; ++j) hb[j] = ((ch.carry & 1) && live) ? ws.carry_b[((size_t)ch.id * DH + j) * np + nr] : 0.f;
+  // the message state entering step t: the chain's initial value at its first step, else the output of step t+1
   auto load_hidden = [&](int t, float(&hv)[DH]) {
-    if (t == ch.t_hi) {
+    if (t == ch.t_top) {
       const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
 #pragma unroll
       for (int j = 0; j < DH; ++j) hv[j] = z;
@@ -999,6 +1007,10 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_reverse_t
     gp_reverse_tc<Ctx, DIN, DH, DH>(c, xt, ob, fvb, amax, kscale, live, o, xinb, Lacc, sw, sG);
 #pragma unroll
     for (int j = 0; j < DH; ++j) hb[j] = xinb[j] + ob[j];
+  }
+  if ((ch.carry & 2) && live) {
+#pragma unroll
+    for (int j = 0; j < DH; ++j) ws.carry_b[((size_t)ch.id * DH + j) * np + nl] = hb[j];
   }
   c.release();
   float sc[DIN + 2 + 2 * DX];
@@ -1049,9 +1061,9 @@ struct LaunchTc {
 
   static cudaError_t fw_reverse(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
                                 const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
-                                TcMats mats, float *spart, int nsc, cudaStream_t st) {
+                                TcMats mats, TimeWin win, float *spart, int nsc, cudaStream_t st) {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
-      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, spart, nsc);
+      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, win, spart, nsc);
     };
     const size_t s1 = TcCtx<DIN, DX, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, true, 0, 2>::bytes(D.M);
     if constexpr (kHas100) {
