@@ -46,6 +46,10 @@ WORKLOADS = {
     "sarcos_m100": dict(dx=14, du=7, dy=7, M=100, S=20, T=250, R=16, kap=50.0, lf=(6.0, 0.0), batch=1894,
                         name="Sarcos-shaped CBF-SSM dx14/du7/dy7 M100 S20 T250 R16 (BASELINE.json configs[2])"),
 }
+# BASELINE.json configs[4] (scaling sweep) corner D=8, M=100, T=500: 2.0 waves of two-tile CTAs; its reverse pass
+# needs ~200 GB of operand tiles and therefore runs in time windows
+WORKLOADS["sweep_d8_m100"] = dict(dx=8, du=1, dy=4, M=100, S=1024, T=500, R=16, kap=1.0, lf=(10.0, 0.0), batch=74,
+                                  name="sweep corner CBF-SSM dx8/du1/dy4 M100 S1024 T500 R16 (BASELINE.json configs[4])")
 WORK = dict(WORKLOADS["robomove_m20"])
 CFG_INIT = dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0)
 

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "cbf_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
     "cbf_timing_enable": (C.c_int, [C.c_int]),
     "cbf_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "cbf_launches_read": (C.c_int, [C.POINTER(C.c_int64), C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -11,6 +11,9 @@
 
 namespace cbf {
 
+static thread_local long long g_launches = 0;
+void cbf_note_launch() { ++g_launches; }
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -308,9 +311,9 @@ static cudaError_t tc_outer(const TcMats &m, int M, int dout, int din, double *r
   const size_t smem = outer_smem_bytes(din);
   cudaError_t e = cudaFuncSetAttribute(tc_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_outer_kernel<<<grid, kOThreads, smem, st>>>(a, rpart);
+  tc_outer_kernel<<<grid, kOThreads, smem, st>>>(a, rpart); cbf_note_launch();
   const int Ctot = M + 2 * dout + din + 1;
-  outer_reduce_kernel<<<ceil_div(M * Ctot, 256), 256, 0, st>>>(rpart, grid, M, dout, din, Rd, accumulate ? 1 : 0);
+  outer_reduce_kernel<<<ceil_div(M * Ctot, 256), 256, 0, st>>>(rpart, grid, M, dout, din, Rd, accumulate ? 1 : 0); cbf_note_launch();
   return cudaGetLastError();
 }
 
@@ -699,7 +702,7 @@ static int elbo_forward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const c
                                                              ws.fpart_fw, st));
   }
   finalize_terms_kernel<<<1, 256, 0, st>>>(ws.fpart_bm, nch * pt, ws.fpart_fw, pt, p.dy, var_y,
-                                           (double)p.D.n_local * p.D.T, ws.stats, terms);
+                                           (double)p.D.n_local * p.D.T, ws.stats, terms); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -766,7 +769,7 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
         CBF_CUDA(p.ops->fw_reverse_tc(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, mf, win, spf, p.nsc_f, st));
       }
       reduce_slots_kernel<<<ceil_div(p.nsc_f, 256), 256, 0, st>>>(spf, p.nspart_f, p.nsc_f, ws.acc_f + p.Lf.scal_off(),
-                                                                  wi > 0 ? 1 : 0);
+                                                                  wi > 0 ? 1 : 0); cbf_note_launch();
       CBF_CUDA(cudaGetLastError());
       ScopedTiming tm(4, st);
       CBF_CUDA(tc_outer(mf, p.D.M, p.dx, p.din, rpart, rdf, wi > 0, st));
@@ -789,18 +792,18 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
                                       spb + (size_t)c0 * pt * p.nsc_b, p.nsc_b, st));
       }
       reduce_slots_kernel<<<ceil_div(p.nsc_b, 256), 256, 0, st>>>(spb, pt * nr, p.nsc_b, ws.acc_b + p.Lb.scal_off(),
-                                                                  ri > 0 ? 1 : 0);
+                                                                  ri > 0 ? 1 : 0); cbf_note_launch();
       CBF_CUDA(cudaGetLastError());
       ScopedTiming tm(5, st);
       CBF_CUDA(tc_outer(mb, p.D.M, p.dh, p.din, rpart, rdb, ri > 0, st));
     }
     finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dx, p.ctot_f, rdf, ws.acc_f + p.Lf.scal_off(), to_dev(gp_f),
                                                grad_flat + gl.f_P, grad_flat + gl.f_alpha, grad_flat + gl.f_S,
-                                               grad_flat + gl.f_Z, grad_flat + gl.f_ell, grad_flat + gl.f_sig2);
+                                               grad_flat + gl.f_Z, grad_flat + gl.f_ell, grad_flat + gl.f_sig2); cbf_note_launch();
     if (!p.half)
       finalize_tc_grad_kernel<<<8, 256, 0, st>>>(p.D.M, p.din, p.dh, p.ctot_b, rdb, ws.acc_b + p.Lb.scal_off(), to_dev(gp_b),
                                                  grad_flat + gl.b_P, grad_flat + gl.b_alpha, grad_flat + gl.b_S,
-                                                 grad_flat + gl.b_Z, grad_flat + gl.b_ell, grad_flat + gl.b_sig2);
+                                                 grad_flat + gl.b_Z, grad_flat + gl.b_ell, grad_flat + gl.b_sig2); cbf_note_launch();
     CBF_CUDA(cudaGetLastError());
   } else {
   // reverse of the forward rollout (writes the y2 adjoints), then of the message chains
@@ -810,7 +813,7 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
     CBF_CUDA(p.ops->fw_reverse(p.D, to_dev(gp_f), var_x, var_y, u, y, eps_f, w_ll, w_kl, ws, ws.gpart_f, grid_f, st));
   }
   reduce_slots_kernel<<<ceil_div(p.Lf.slot(), 256), 256, 0, st>>>(ws.gpart_f, grid_f * p.slots_per_cta, p.Lf.slot(),
-                                                                  ws.acc_f);
+                                                                  ws.acc_f); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
 
   int nslots_b = 0;
@@ -829,25 +832,25 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
     nslots_b += grid_b;
   }
   reduce_slots_kernel<<<ceil_div(p.Lb.slot(), 256), 256, 0, st>>>(ws.gpart_b, nslots_b * p.slots_per_cta, p.Lb.slot(),
-                                                                  ws.acc_b);
+                                                                  ws.acc_b); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
 
   finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lf, ws.acc_f, to_dev(gp_f), grad_flat + gl.f_P, grad_flat + gl.f_alpha,
                                              grad_flat + gl.f_S, grad_flat + gl.f_Z, grad_flat + gl.f_ell,
-                                             grad_flat + gl.f_sig2);
+                                             grad_flat + gl.f_sig2); cbf_note_launch();
   if (!p.half)
     finalize_gp_grad_kernel<<<8, 256, 0, st>>>(p.Lb, ws.acc_b, to_dev(gp_b), grad_flat + gl.b_P, grad_flat + gl.b_alpha,
                                                grad_flat + gl.b_S, grad_flat + gl.b_Z, grad_flat + gl.b_ell,
-                                               grad_flat + gl.b_sig2);
+                                               grad_flat + gl.b_sig2); cbf_note_launch();
   }
   if (p.half) {   // no backward-message GP: its block of the flat gradient is zero; x_0 adjoint per sequence
     CBF_CUDA(cudaMemsetAsync(grad_flat + gl.b_P, 0, sizeof(double) * (size_t)(gl.var_x - gl.b_P), st));
     const int nb = p.D.n_local / p.D.S;
-    reduce_x0b_kernel<<<ceil_div(nb * p.dx, 256), 256, 0, st>>>(ws.x0b, ws.npad, p.D.S, nb, p.dx, x0_bar);
+    reduce_x0b_kernel<<<ceil_div(nb * p.dx, 256), 256, 0, st>>>(ws.x0b, ws.npad, p.D.S, nb, p.dx, x0_bar); cbf_note_launch();
   }
   finalize_noise_grad_kernel<<<1, 32 * ceil_div(p.dx, 32), 0, st>>>(
       p.dx, p.dy, p.din, ws.acc_f + p.Lf.scal_off(), ws.acc_b + p.Lb.scal_off(), ws.stats, var_y, (double)term_weights_host[0],
-      (double)p.D.n_local * p.D.T, grad_flat + gl.var_x, grad_flat + gl.var_y);
+      (double)p.D.n_local * p.D.T, grad_flat + gl.var_x, grad_flat + gl.var_y); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -886,7 +889,7 @@ CBF_API int cbf_export_states(const cbf_shape *shape, const float *y, float *x_f
   const size_t total = (size_t)p.D.n_local * p.D.T * p.dx;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  export_states_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p.D, p.dx, p.dy, y, ws, x_final, y_tilde);
+  export_states_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p.D, p.dx, p.dy, y, ws, x_final, y_tilde); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -900,7 +903,7 @@ CBF_API int cbf_moments(const float *x, int32_t nb, int32_t T, int32_t S, int32_
   }
   const int rows = nb * T;
   moments_kernel<<<ceil_div(rows * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, S, d, d_keep,
-                                                                                         add_var, mean, var);
+                                                                                         add_var, mean, var); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -911,7 +914,7 @@ CBF_API int cbf_adam_step(int64_t n, double *theta, const double *grad, double *
   if (n < 1 || step < 1) { set_error("cbf_adam_step: invalid n/step"); return CBF_ERR_INVALID_SHAPE; }
   const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, theta, grad, m, v, lr_t,
-                                                                                         beta1, beta2, eps);
+                                                                                         beta1, beta2, eps); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -937,12 +940,19 @@ CBF_API int cbf_timing_read(double *ms_sum_host, int64_t *count_host) {
   return 0;
 }
 
+CBF_API int cbf_launches_read(int64_t *count_host, int reset) {
+  if (!count_host) { set_error("cbf_launches_read: NULL argument"); return CBF_ERR_NULL; }
+  *count_host = (int64_t)g_launches;
+  if (reset) g_launches = 0;
+  return 0;
+}
+
 CBF_API int cbf_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t stream_id, void *stream) {
   if (!out) { set_error("cbf_fill_normal: NULL argument"); return CBF_ERR_NULL; }
   if (n < 1) return 0;
   const int64_t quads = (n + 3) / 4;
   fill_normal_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed,
-                                                                                                    stream_id);
+                                                                                                    stream_id); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -7,6 +7,10 @@
 
 namespace cbf {
 
+// Counts the kernel launches of this library on the calling host thread (cbf_launches_read; bench.py's
+// gpu_launches).  Defined in api.cu.
+void cbf_note_launch();
+
 constexpr int kNP = 32;          // particles per CTA tile in the cooperative (generic) path
 constexpr int kLD = kNP + 4;     // row stride of the [m][n] shared arrays (== 4 mod 32: conflict-free float4 rows)
 constexpr int kMaxChains = 120;  // chain segments per launch (kernel parameter space)

@@ -1063,7 +1063,7 @@ struct LaunchTc {
                                 const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
                                 TcMats mats, TimeWin win, float *spart, int nsc, cudaStream_t st) {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
-      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, win, spart, nsc);
+      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, win, spart, nsc); cbf_note_launch();
     };
     const size_t s1 = TcCtx<DIN, DX, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, true, 0, 2>::bytes(D.M);
     if constexpr (kHas100) {
@@ -1079,7 +1079,7 @@ struct LaunchTc {
                                 TcMats mats, float *spart, int nsc, cudaStream_t st) {
     if (ct.count == 0) return cudaSuccess;
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
-      kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats, spart, nsc);
+      kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats, spart, nsc); cbf_note_launch();
     };
     const size_t s1 = TcCtx<DIN, DH, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, true, 0, 2>::bytes(D.M);
     if constexpr (kHas100) {
@@ -1096,7 +1096,7 @@ struct LaunchTc {
                                 float *part_out, cudaStream_t st) {
     if (ct.count == 0) return cudaSuccess;
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
-      kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
+      kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out); cbf_note_launch();
     };
     const size_t s1 = TcCtx<DIN, DH, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, false, 0, 2>::bytes(D.M);
     if constexpr (kHas100) {
@@ -1111,7 +1111,7 @@ struct LaunchTc {
                                 const float *y, const float *eps_f, Workspace ws, float *part_out,
                                 cudaStream_t st) {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
-      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, ws, part_out);
+      kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, ws, part_out); cbf_note_launch();
     };
     const size_t s1 = TcCtx<DIN, DX, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, false, 0, 2>::bytes(D.M);
     if constexpr (kHas100) {

@@ -35,7 +35,7 @@ struct LaunchFast {
   // Refresh the constant-bank image of one GP (slot 0: forward-rollout GP, 1: message GP).
   static cudaError_t load_const(int slot, GpDev gp, int dout, float *scratch, cudaStream_t st) {
     if (!kConstOps) return cudaSuccess;
-    pack_const_kernel<<<1, 256, 0, st>>>(gp, M, DIN, dout, scratch);
+    pack_const_kernel<<<1, 256, 0, st>>>(gp, M, DIN, dout, scratch); cbf_note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t bytes = sizeof(float) * (slot == 0 ? Gf::C::TOTAL : Gb::C::TOTAL);
@@ -52,7 +52,7 @@ struct LaunchFast {
     if (e != cudaSuccess) return e;
     if ((e = load_const(1, gp, DH, ws.cpack + kConstFloats, st)) != cudaSuccess) return e;
     dim3 grid(ceil_div(D.n_local, kFastThreads), ct.count);
-    bm_forward_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
+    bm_forward_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out); cbf_note_launch();
     return cudaGetLastError();
   }
 
@@ -64,7 +64,7 @@ struct LaunchFast {
     if (e != cudaSuccess) return e;
     if ((e = load_const(0, gp, DX, ws.cpack, st)) != cudaSuccess) return e;
     fw_forward_fast_kernel<DX, DU, DY, M><<<ceil_div(D.n_local, kFastThreads), kFastThreads, smem, st>>>(
-        D, gp, vx, vy, u, y, eps_f, ws, part_out);
+        D, gp, vx, vy, u, y, eps_f, ws, part_out); cbf_note_launch();
     return cudaGetLastError();
   }
 
@@ -78,7 +78,7 @@ struct LaunchFast {
     AccLayout Lf, Lb;
     layouts(M, &Lf, &Lb);
     fw_reverse_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws,
-                                                                           part_out, Lf.slot());
+                                                                           part_out, Lf.slot()); cbf_note_launch();
     return cudaGetLastError();
   }
 
@@ -92,7 +92,7 @@ struct LaunchFast {
     AccLayout Lf, Lb;
     layouts(M, &Lf, &Lb);
     bm_reverse_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws,
-                                                                           part_out, Lb.slot());
+                                                                           part_out, Lb.slot()); cbf_note_launch();
     return cudaGetLastError();
   }
 

@@ -49,7 +49,7 @@ struct Launch {
     cudaError_t e = prep(bm_forward_kernel<DX, DU, DY>, smem);
     if (e != cudaSuccess) return e;
     dim3 grid(ceil_div(D.n_local, kNP), ct.count);
-    bm_forward_kernel<DX, DU, DY><<<grid, 32 * coop_parts(D.M), smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out);
+    bm_forward_kernel<DX, DU, DY><<<grid, 32 * coop_parts(D.M), smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out); cbf_note_launch();
     return cudaGetLastError();
   }
 
@@ -60,7 +60,7 @@ struct Launch {
     cudaError_t e = prep(fw_forward_kernel<DX, DU, DY>, smem);
     if (e != cudaSuccess) return e;
     fw_forward_kernel<DX, DU, DY><<<ceil_div(D.n_local, kNP), 32 * coop_parts(D.M), smem, st>>>(
-        D, gp, vx, vy, u, y, eps_f, ws, part_out);
+        D, gp, vx, vy, u, y, eps_f, ws, part_out); cbf_note_launch();
     return cudaGetLastError();
   }
 
@@ -71,7 +71,7 @@ struct Launch {
     cudaError_t e = prep(fw_reverse_kernel<DX, DU, DY>, smem);
     if (e != cudaSuccess) return e;
     fw_reverse_kernel<DX, DU, DY><<<grid, 32 * coop_parts(D.M), smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl,
-                                                                            ws, part_out);
+                                                                            ws, part_out); cbf_note_launch();
     return cudaGetLastError();
   }
 
@@ -82,7 +82,7 @@ struct Launch {
     cudaError_t e = prep(bm_reverse_kernel<DX, DU, DY>, smem);
     if (e != cudaSuccess) return e;
     bm_reverse_kernel<DX, DU, DY><<<grid, 32 * coop_parts(D.M), smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws,
-                                                                            part_out);
+                                                                            part_out); cbf_note_launch();
     return cudaGetLastError();
   }
 

@@ -284,7 +284,7 @@ CBF_API int cbf_gp_prologue(int32_t M, int32_t Din, int32_t Dout, const double *
   if (M < 1 || Din < 1 || Dout < 1) { set_error("cbf_gp_prologue: invalid shape"); return CBF_ERR_INVALID_SHAPE; }
   gp_prologue_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(M, Din, Dout, zeta_pos, zeta_mean, zeta_var_unc,
                                                                       variance_unc, lengthscales_unc, Z32, ell32,
-                                                                      sig232, P32, alpha32, S32, kl_out, state);
+                                                                      sig232, P32, alpha32, S32, kl_out, state); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -302,7 +302,7 @@ CBF_API int cbf_gp_prologue_backward(int32_t M, int32_t Din, int32_t Dout, const
   if (M < 1 || Din < 1 || Dout < 1) { set_error("cbf_gp_prologue_backward: invalid shape"); return CBF_ERR_INVALID_SHAPE; }
   gp_prologue_backward_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(
       M, Din, Dout, gP, galpha, gS, gZ, gell, gsig2, kl_weight, state, g_zeta_pos, g_zeta_mean,
-      g_zeta_var_unc, g_variance_unc, g_lengthscales_unc);
+      g_zeta_var_unc, g_variance_unc, g_lengthscales_unc); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -312,7 +312,7 @@ CBF_API int cbf_noise_forward(int32_t dx, const double *var_x_unc, const double 
   if (!var_x_unc || !var_y_unc || !var_x32 || !var_y32) { set_error("cbf_noise_forward: NULL argument"); return CBF_ERR_NULL; }
   if (dx < 1 || dx > 1024) { set_error("cbf_noise_forward: invalid dx"); return CBF_ERR_INVALID_SHAPE; }
   noise_forward_kernel<<<1, round_up(dx, 32), 0, static_cast<cudaStream_t>(stream)>>>(dx, var_x_unc, var_y_unc, var_x32,
-                                                                                     var_y32);
+                                                                                     var_y32); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -325,7 +325,7 @@ CBF_API int cbf_noise_backward(int32_t dx, const double *var_x_unc, const double
   }
   if (dx < 1 || dx > 1024) { set_error("cbf_noise_backward: invalid dx"); return CBF_ERR_INVALID_SHAPE; }
   noise_backward_kernel<<<1, round_up(dx, 32), 0, static_cast<cudaStream_t>(stream)>>>(dx, var_x_unc, var_y_unc, g_var_x,
-                                                                                      g_var_y, g_var_x_unc, g_var_y_unc);
+                                                                                      g_var_y, g_var_x_unc, g_var_y_unc); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }

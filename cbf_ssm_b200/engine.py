@@ -159,12 +159,12 @@ class ElboEngine:
         self._ws = None
         self._ws_key = None
         self._side = None
+        self._launch_base = 0
         self._gl = None
         self._gflat = None
         self._shape = None
         self._saved = None
         self.flags = 0             # CBF_FLAG_* passed in cbf_shape.flags
-        self.launches = 0          # kernels of this library launched so far (bench.py gpu_launches)
 
     # ---------------- parameters ----------------
     def view(self, name, of=None):
@@ -183,6 +183,20 @@ class ElboEngine:
         return {n: self.view(n, self.grad).detach().cpu().numpy().copy() for n in self.names}
 
     # ---------------- plumbing ----------------
+    @property
+    def launches(self):
+        """Kernels of this library launched on this host thread since the counter was last set (the library
+        counts every launch itself: cbf_launches_read; bench.py's gpu_launches)."""
+        n = C.c_int64(0)
+        check(self.lib.cbf_launches_read(C.byref(n), 0))
+        return int(n.value) + self._launch_base
+
+    @launches.setter
+    def launches(self, value):
+        n = C.c_int64(0)
+        check(self.lib.cbf_launches_read(C.byref(n), 1))
+        self._launch_base = int(value)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -234,7 +248,6 @@ class ElboEngine:
                                         ptr(self.var_x), ptr(self._scratch32), st))
             check(lib.cbf_noise_forward(d.dim_y, ptr(self.view("var_y_unc")), ptr(self.view("var_y_unc")),
                                         ptr(self.var_y), ptr(self._scratch32), st))
-            self.launches += 1
         else:
             check(lib.cbf_noise_forward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
                                         ptr(self.var_x), ptr(self.var_y), st))
@@ -244,7 +257,6 @@ class ElboEngine:
                 check(lib.cbf_gp_prologue(g.M, g.din, g.dout, *(ptr(self.view(f"{tag}.{f}")) for f in GP_FIELDS),
                                           ptr(g.Z), ptr(g.ell), ptr(g.sig2), ptr(g.P), ptr(g.alpha), ptr(g.S),
                                           ptr(g.kl), ptr(g.state), s2))
-        self.launches += 2 if d.half else 3
 
     def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True, x0=None):
         """u [B,T,du], y [B,T,dy] float32 device tensors; draws float32 device tensors
@@ -268,10 +280,6 @@ class ElboEngine:
                                             ptr(eps_f), ptr(self.terms), ptr(self._ws), self._stream()))
         self._shape = shape
         self._saved = (u, y, eps_b, z_b, eps_f, x0)
-        self._nb = 0 if self.dims.half else count_chain_batches(T, self.dims.recog_len)
-        # register path: one operand-pack kernel in front of each rollout kernel
-        self._packs = 1 if (self.kernel_path == 2 and not (self.flags & 1)) else 0
-        self.launches += self._nb * (1 + self._packs) + 1 + self._packs + 1
         return self.loss_terms(self.terms)
 
     def loss_terms(self, terms):
@@ -329,7 +337,6 @@ class ElboEngine:
         else:
             check(lib.cbf_noise_backward(d.dim_x, ptr(self.view("var_x_unc")), ptr(self.view("var_y_unc")),
                                          at(gl.var_x), at(gl.var_y), gat("var_x_unc"), gat("var_y_unc"), st))
-        self.launches += 6 + self._nb * (1 + self._packs) + self._packs + (3 if not d.half else 4)
         return self.grad
 
     def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -337,7 +344,6 @@ class ElboEngine:
         self.adam_t += 1
         check(self.lib.cbf_adam_step(self.theta.numel(), ptr(self.theta), ptr(self.grad), ptr(self.adam_m),
                                      ptr(self.adam_v), self.adam_t, float(lr), beta1, beta2, eps, self._stream()))
-        self.launches += 1
 
     def export_states(self, y):
         """x_final, y_tilde as [nb, T, S, dx] float32 (cbfssm.py:97,181) of the last forward."""
@@ -358,7 +364,6 @@ class ElboEngine:
 
     def fill_normal(self, out, seed, stream_id):
         check(self.lib.cbf_fill_normal(ptr(out), out.numel(), int(seed), int(stream_id), self._stream()))
-        self.launches += 1
         return out
 
     def kernel_level_grads(self):

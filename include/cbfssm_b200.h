@@ -204,6 +204,10 @@ CBF_API int cbf_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t strea
 CBF_API int cbf_timing_enable(int enable);
 CBF_API int cbf_timing_read(double *ms_sum_host /*[8]*/, int64_t *count_host /*[8]*/);
 
+/* Number of kernels this library has launched on the calling host thread since the last reset
+ * (measurement aid: bench.py's gpu_launches; there is no reference counterpart). */
+CBF_API int cbf_launches_read(int64_t *count_host, int reset);
+
 #ifdef __cplusplus
 }
 #endif
