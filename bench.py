@@ -50,6 +50,13 @@ WORKLOADS = {
 # needs ~200 GB of operand tiles and therefore runs in time windows
 WORKLOADS["sweep_d8_m100"] = dict(dx=8, du=1, dy=4, M=100, S=1024, T=500, R=16, kap=1.0, lf=(10.0, 0.0), batch=74,
                                   name="sweep corner CBF-SSM dx8/du1/dy4 M100 S1024 T500 R16 (BASELINE.json configs[4])")
+# BASELINE.json configs[3]: Voliro-shaped multi-experiment windows, 256 sequences x 1024 particles per GPU
+WORKLOADS["voliro_m20"] = dict(dx=13, du=6, dy=7, M=20, S=1024, T=64, R=16, kap=1.0, lf=(20.0, 0.0), batch=256,
+                               name="Voliro-shaped CBF-SSM dx13/du6/dy7 M20 S1024 T64 R16 (BASELINE.json configs[3])")
+# BASELINE.json configs[0]: SpringNonLinear with the run/template.py defaults at the reference's own batch size
+WORKLOADS["spring_template_b32"] = dict(dx=4, du=1, dy=1, M=100, S=50, T=100, R=50, kap=1.0, lf=(10.0, 0.0), batch=32,
+                                        name="SpringNonLinear run/template.py defaults dx4/du1/dy1 M100 S50 T100 R50, B=32 "
+                                             "(BASELINE.json configs[0])")
 WORK = dict(WORKLOADS["robomove_m20"])
 CFG_INIT = dict(zeta_pos=2.0, zeta_mean=0.01, zeta_var=1e-4, gp_var=0.01, gp_len=1.0)
 
