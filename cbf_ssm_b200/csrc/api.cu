@@ -75,8 +75,11 @@ struct ScopedTiming {
 
 constexpr int kMaxGridRev = 148 * 8;   // upper bound on persistent reverse CTAs (workspace sizing)
 constexpr size_t kMaxSmem = 227 * 1024;
-constexpr int kMinParticlesRegisterPath = 4096;   // one-thread-per-particle kernels below this are latency-bound
-constexpr int kMinParticlesTensorPath = 4096;     // 128-particle tcgen05 tiles: faster from ~32 CTAs (tools/bench_cross.sh)
+// Particle counts from which the specialised paths are used.  With the final kernels both beat the cooperative
+// path at every size measured (M=20: 3.0 vs 3.2-3.9 ms/step at 50-3 200 particles; M=100: 5.2 vs 7.7 ms at
+// 50-3 200 particles, tools/bench_cross.sh), so the cooperative kernels serve only M without a specialised path.
+constexpr int kMinParticlesRegisterPath = 1;
+constexpr int kMinParticlesTensorPath = 1;
 
 // Live chain segments of both backward-message runs (cbfssm.py:123-136, SURVEY 8a note 5).
 static std::vector<Chain> build_chains(int T, int R) {

@@ -63,9 +63,9 @@ typedef struct cbf_shape {
 #define CBF_FLAG_FORCE_COOPERATIVE 1
 /* Do not use the tcgen05 tensor-core forward kernels (selected by default for 48 <= M <= 128). */
 #define CBF_FLAG_NO_TENSOR_CORES 2
-/* By default the register-resident kernels are used from 4096 particles per call and the
- * tensor-core kernels from 4096 as well (below that the cooperative kernels have the lower
- * latency per time step).  These flags select them regardless of the particle count. */
+/* The register-resident kernels (compiled-in small M) and the tensor-core kernels (48 <= M <= 128) are the
+ * default at every particle count; the cooperative kernels serve every other M.  These flags select a
+ * specialised path explicitly (they fail if it does not exist for the shape). */
 #define CBF_FLAG_FORCE_REGISTER 4
 #define CBF_FLAG_FORCE_TENSOR_CORES 8
 /* CBFSSMHALF (cbfssm/model/cbfssmhalf.py): no backward-message GP, x_0 supplied by the caller's
