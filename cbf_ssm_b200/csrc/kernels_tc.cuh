@@ -165,7 +165,7 @@ struct TcCtx {
     // The reverse pass reuses the K operand buffers for b (k is re-read from the float32 operand
     // matrix it was just written to, an L2 hit), which keeps the CTA at ~114 KB: two CTAs per SM.
     B1 = K1; B2 = K2;
-    // The tables have MP rows: rows >= M hold Z/ell = 1e18 (squared distance ~1e37, so k'' underflows to an
+    // The tables have MP rows (Zt holds -Z/ell so that delta is one packed add): rows >= M hold Z/ell = 1e18 (squared distance ~1e37, so k'' underflows to an
     // exact 0 and never wins the minimum) and alpha = S = 0, which makes every padded row contribute exact
     // zeros everywhere -- the per-row loops need no m < M guards.
     float *Zw = reinterpret_cast<float *>(base); base += sizeof(float) * MP * DINP;
@@ -200,7 +200,7 @@ struct TcCtx {
     }
     for (int i = tid; i < MP * DINP; i += nt) {
       const int r = i / DINP, c = i % DINP;
-      Zw[i] = (c < DIN) ? (r < M ? g.Z[r * DIN + c] / g.ell[c] : 1e18f) : 0.f;
+      Zw[i] = (c < DIN) ? (r < M ? -g.Z[r * DIN + c] / g.ell[c] : -1e18f) : 0.f;   // -Z/ell: delta = x~ + Zt
     }
     for (int i = tid; i < MP * DOUTP; i += nt) {
       const int r = i / DOUTP, c = i % DOUTP;
@@ -399,8 +399,13 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
     for (int j = 0; j < DINP; ++j) xt[j] = (j < DIN) ? xin[j < DIN ? j : 0] * il[j] : 0.f;
   }
+  // packed FP32 (FADD2 / FFMA2 / FMUL2): pairs of input dims for delta, pairs of output dims for the sums
+  constexpr int J2 = (DIN + 1) / 2, D2 = (DOUT + 1) / 2;
+  unsigned long long x2[J2], fm2[D2], fv2[D2];
 #pragma unroll
-  for (int d = 0; d < DOUT; ++d) fm[d] = 0.f;
+  for (int j = 0; j < J2; ++j) x2[j] = pack2(xt[2 * j], xt[2 * j + 1]);   // xt is zero-padded to DINP
+#pragma unroll
+  for (int d = 0; d < D2; ++d) { fm2[d] = 0ull; fv2[d] = 0ull; }
   // ---- kernel vector -> fp16 split operands ----
   // fp16 has a narrow exponent range and k' = exp(-d^2/2) can be 1e-12 for every inducing point (e.g.
   // 21 input dims), so each particle's vector is normalised by its own maximum: pass 1 parks the squared
@@ -415,9 +420,13 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       const int m = ch * 8 + e;
       float z[DINP];
       ld_row<DINP>(c.Zt + m * DINP, z);
-      float d2 = 0.f;
+      unsigned long long acc = 0ull;
 #pragma unroll
-      for (int j = 0; j < DIN; ++j) { const float dl = xt[j] - z[j]; d2 = fmaf(dl, dl, d2); }
+      for (int j = 0; j < J2; ++j) {
+        const unsigned long long dl = add2(x2[j], pack2(z[2 * j], z[2 * j + 1]));
+        acc = fma2(dl, dl, acc);
+      }
+      const float d2 = hsum2(acc);
       d2min = fminf(d2min, d2);
       dv[e] = d2;
     }
@@ -438,8 +447,9 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       const float kp = fast_exp2(kNegHalfLog2e * (dv[e] - d2min));
       float al[DOUTP];
       ld_row<DOUTP>(c.al + m * DOUTP, al);
+      const unsigned long long kk = pack2(kp, kp);
 #pragma unroll
-      for (int d = 0; d < DOUT; ++d) fm[d] = fmaf(kp, al[d], fm[d]);
+      for (int d = 0; d < D2; ++d) fm2[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2[d]);
       kv[e] = kp;
     }
     tc_write_row8(c.K1, c.K2, t, ch, kv);
@@ -455,8 +465,6 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   // ---- accumulator row back: q' = k'.a', v'_d = sum a'^2 S ----
   float q = 0.f;
   amax = 0.f;
-#pragma unroll
-  for (int d = 0; d < DOUT; ++d) fv[d] = 0.f;
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
   uint32_t ra[16];
   tmem_ld16_issue(trow, ra);
@@ -476,9 +484,18 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       const float a2 = a[e] * a[e];
       float S[DOUTP];
       ld_row<DOUTP>(c.Sm + m * DOUTP, S);
+      const unsigned long long aa = pack2(a2, a2);
 #pragma unroll
-      for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, S[d], fv[d]);
+      for (int d = 0; d < D2; ++d) fv2[d] = fma2(pack2(S[2 * d], S[2 * d + 1]), aa, fv2[d]);
     }
+  }
+#pragma unroll
+  for (int d = 0; d < D2; ++d) {
+    float m0, m1, v0, v1;
+    unpack2(fm2[d], m0, m1);
+    unpack2(fv2[d], v0, v1);
+    fm[2 * d] = m0; fv[2 * d] = v0;
+    if (2 * d + 1 < DOUT) { fm[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = m1; fv[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = v1; }
   }
   // q, fv, amax were formed from the normalised k'' and a'' = P' k''; undo the per-particle scale
   const float s4 = c.sig2 * c.sig2, ps = c.pscale, k2 = kscale * kscale;
@@ -563,8 +580,12 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   // ---- k_bar = alpha gm + 2 P b - 2 G a ; w = k_bar k ; a_bar = 2 b - G k ----
   const float pbs = ps * ascale * binv;         // (P b)_m = pbs * (P' b'')_m
   const float bs = ascale * binv;               // b_m = bs * b''_m
+  constexpr int J2 = (DIN + 1) / 2, N2 = (NEED + 1) / 2;
+  unsigned long long x2[J2], xs2[N2], L2[J2];   // packed over input-dim pairs (2j, 2j+1)
 #pragma unroll
-  for (int j = 0; j < NEED; ++j) xinb[j] = 0.f;
+  for (int j = 0; j < J2; ++j) { x2[j] = pack2(xt[2 * j], xt[2 * j + 1]); L2[j] = 0ull; }
+#pragma unroll
+  for (int j = 0; j < N2; ++j) xs2[j] = 0ull;
 #pragma unroll(MC ? 1 : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float pb[16], a[16], kp[16], bb[16];
@@ -601,12 +622,13 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       sw += w;
       float z[DINP];
       ld_row<DINP>(c.Zt + m * DINP, z);
+      const unsigned long long ww = pack2(w, w);
 #pragma unroll
-      for (int j = 0; j < DIN; ++j) {
-        const float dl = xt[j] - z[j];
-        const float wd = w * dl;
-        if (j < NEED) xinb[j < NEED ? j : 0] -= wd;
-        Lacc[j] = fmaf(wd, dl, Lacc[j]);
+      for (int j = 0; j < J2; ++j) {
+        const unsigned long long dl = add2(x2[j], pack2(z[2 * j], z[2 * j + 1]));
+        const unsigned long long wd = mul2(dl, ww);
+        if (j < N2) xs2[j < N2 ? j : 0] = add2(xs2[j < N2 ? j : 0], wd);
+        L2[j] = fma2(wd, dl, L2[j]);
       }
       wv[e] = w;
       abv[e] = 2.f * bs * bb[e] - Gs * k;
@@ -623,11 +645,23 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       if (2 * cc + 1 < o.MB) o.put8(o.bAb + 2 * cc + 1, hi);
     }
   }
+#pragma unroll
+  for (int j = 0; j < J2; ++j) {
+    float l0, l1;
+    unpack2(L2[j], l0, l1);
+    Lacc[2 * j] += l0;
+    if (2 * j + 1 < DIN) Lacc[2 * j + 1 < DIN ? 2 * j + 1 : 0] += l1;
+  }
   {
     float il[DINP];
     ld_row<DINP>(c.il, il);
 #pragma unroll
-    for (int j = 0; j < NEED; ++j) xinb[j] *= il[j];
+    for (int j = 0; j < N2; ++j) {
+      float s0, s1;
+      unpack2(xs2[j], s0, s1);
+      xinb[2 * j] = -s0 * il[2 * j];
+      if (2 * j + 1 < NEED) xinb[2 * j + 1 < NEED ? 2 * j + 1 : 0] = -s1 * il[2 * j + 1];
+    }
   }
   tc_fence_before();
 }
