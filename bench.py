@@ -328,7 +328,7 @@ def run_b200(args):
                 "whole_step_frac": step_frac,
                 **({"note": "tensor path: the M^2 contractions run on tcgen05 (fp16/bf16 splits, 3 MMA passes), so "
                             "algorithmic FLOPs against the FP32-SIMT peak can exceed 1; the kernels are bound by the "
-                            "O(M*D) SIMT work at 8 warps/SM (profiles/r01h_m100_*)"} if kcnt[4] else {}),
+                            "O(M*D) SIMT work at 8 warps/SM (profiles/r01i_m100_*)"} if kcnt[4] else {}),
                 "hbm": {"algorithmic_bytes_per_particle_step": bytes_pstep,
                         "achieved_gbs": bytes_pstep * psteps_local / (ms_per_step * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs")}}

@@ -2,7 +2,7 @@
 # Round-end evidence run (one B200): full GPU test suite, the two bench workloads, ncu launch lists and
 # --set full captures of the dominant kernels at the bench batch sizes. Outputs under gpurun_out/final/.
 set -u
-O=gpurun_out/final3; mkdir -p $O
+O=gpurun_out/final4; mkdir -p $O
 python -m pytest tests -x -q -m gpu > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log; tail -3 $O/pytest.log
 python bench.py > $O/bench_m20.json 2> $O/bench_m20.err; tail -c 600 $O/bench_m20.json
 python bench.py --workload template_m100 --no-cpu-baseline > $O/bench_m100.json 2> $O/bench_m100.err; tail -c 600 $O/bench_m100.json
