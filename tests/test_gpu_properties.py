@@ -69,6 +69,35 @@ def test_sum_of_particle_shards_equals_the_whole_at_bench_shape(flags):
     assert rel_inf(acc[:gl].cpu().numpy(), whole[:gl].cpu().numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("dims", [(4, 2, 2), (8, 1, 4)], ids=["dx4_one_tile_ctas", "dx8_two_tile_ctas"])
+def test_tensor_path_shards_add_up(dims, monkeypatch):
+    """The same contract on the tcgen05 path (M=100): ragged particle shards with n_offset != 0, the reverse
+    pass in several time windows, one- and two-tile CTAs."""
+    monkeypatch.setenv("CBFSSM_B200_TC_WINDOW_BYTES", str(40_000_000))
+    dx, du, dy = dims
+    eng = _engine(dx=dx, du=du, dy=dy, M=100, S=50, R=10, lf=(10.0, 0.5))
+    eng.flags = 12
+    B, T = 24, 40
+    u, y, eb, zb, ef = _inputs(eng, B, T)
+    N = B * eng.dims.samples
+    eng.forward(u, y, eb, zb, ef, True)
+    eng.backward()
+    whole_terms, whole = eng.terms[:3].clone(), eng._gflat.clone()
+    acc, tacc = torch.zeros_like(whole), torch.zeros_like(whole_terms)
+    bounds = [0, 130, 517, 1000, N]            # shards that are not multiples of the 128-particle tile
+    for n0, n1 in zip(bounds[:-1], bounds[1:]):
+        sl = slice(n0, n1)
+        eng.forward(u, y, eb[:, :, sl].contiguous(), zb[:, :, sl].contiguous(), ef[:, sl].contiguous(), True,
+                    n_offset=n0, n_local=n1 - n0)
+        eng.backward()
+        acc += eng._gflat
+        tacc += eng.terms[:3]
+    torch.cuda.synchronize()
+    gl = eng._gl.total
+    assert rel_inf(tacc.cpu().numpy(), whole_terms.cpu().numpy()) < 1e-6
+    assert rel_inf(acc[:gl].cpu().numpy(), whole[:gl].cpu().numpy()) < 5e-5
+
+
 def test_loss_is_linear_in_the_loss_factors():
     """loss = -(l1/S)(loglik - kl_x) - (l2/S) entropy + kl_z  (cbfssm.py:257-262)."""
     e1 = _engine(lf=(20.0, 0.0))
