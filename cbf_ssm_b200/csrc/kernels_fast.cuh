@@ -378,7 +378,10 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
 //   right matrix, column space of the accumulators  [k | g_mean | g_var | x~,1] (blocks padded to
 //     TC): stored pair-interleaved, element (col, n) at (col/2)*kPS + 2n + (col&1), so one
 //     LDS.128 yields two particles x two adjacent columns = two FFMA2 operand pairs;
-//   left arrays [a_bar | k | a^2 | w], K-major: element (m, n) at (which*LROWS + m)*kSLD + n.
+//   left arrays [a_bar | k | a^2 | w], K-major: element (m, n) at which*LSTR + m*kSLD + n; LSTR = 8 mod 32
+//     floats, so the four arrays start 8 banks apart: the lanes of a quarter warp (same row group, different
+//     arrays) hit disjoint banks with their 128-bit loads (a_bar and a^2 collided before: 22 % of the
+//     shared-memory wavefronts were conflicts).
 constexpr int kPS = 68;   // pair-row stride (floats): 64 + 4
 template <int M, int DIN, int DOUT>
 struct WarpAcc {
@@ -389,8 +392,9 @@ struct WarpAcc {
   static constexpr int CG = CGk + 2 * CGd + CGx, NTILES = RG * CG, NCOLS = CG * TC;
   static constexpr int colK = 0, colGm = CGk * TC, colGv = colGm + CGd * TC, colX = colGv + CGd * TC;
   static constexpr int LROWS = RG * TR;
+  static constexpr int LSTR = LROWS * kSLD + (8 - (LROWS * kSLD) % 32 + 32) % 32;
   static constexpr int LEFT_OFF = (NCOLS / 2) * kPS;
-  static constexpr int FLOATS = LEFT_OFF + 4 * LROWS * kSLD;
+  static constexpr int FLOATS = LEFT_OFF + 4 * LSTR;
   static constexpr int NACC = NTILES * TR * TC;
   enum { L_AB = 0, L_K = 1, L_ASQ = 2, L_W = 3 };
 
@@ -398,7 +402,7 @@ struct WarpAcc {
   int loff[ROUNDS], roff[ROUNDS];   // staging offsets (floats) of this lane's tiles
 
   static __device__ __forceinline__ void put_left(float *stg, int lane, int which, int m, float v) {
-    stg[LEFT_OFF + (which * LROWS + m) * kSLD + lane] = v;
+    stg[LEFT_OFF + which * LSTR + m * kSLD + lane] = v;
   }
   // columns col0 .. col0+N-1 of the right matrix (col0 even), two per 64-bit store
   template <int N, int NMAX>
@@ -425,7 +429,7 @@ struct WarpAcc {
       else if (cg < CGk + CGd) which = L_K;
       else if (cg < CGk + 2 * CGd) which = L_ASQ;
       else which = L_W;
-      loff[r] = LEFT_OFF + (which * LROWS + rg * TR) * kSLD;
+      loff[r] = LEFT_OFF + which * LSTR + rg * TR * kSLD;
       roff[r] = (cg * TC / 2) * kPS;
     }
   }
