@@ -383,6 +383,10 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
 //     arrays) hit disjoint banks with their 128-bit loads (a_bar and a^2 collided before: 22 % of the
 //     shared-memory wavefronts were conflicts).
 constexpr int kPS = 68;   // pair-row stride (floats): 64 + 4
+#ifndef CBF_ACC_UNROLL
+#define CBF_ACC_UNROLL 2
+#endif
+constexpr int kAccUnroll = CBF_ACC_UNROLL;   // unroll of the 8-iteration particle loop of the accumulation
 template <int M, int DIN, int DOUT>
 struct WarpAcc {
   static constexpr TileCfg TCFG = pick_tiles(M, DIN, DOUT);
@@ -439,7 +443,7 @@ struct WarpAcc {
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
       const float *lp = stg + loff[r], *rp = stg + roff[r];
-#pragma unroll 2
+#pragma unroll(kAccUnroll)
       for (int n4 = 0; n4 < 32; n4 += 4) {
         float4 l[TR], r0[TC2], r1[TC2];
 #pragma unroll
