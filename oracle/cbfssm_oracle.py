@@ -11,7 +11,7 @@ therefore a float64 op-for-op *restatement* of the reference files cited on each
 function, with every ``tf.random_normal`` draw turned into an explicit input so
 that results are reproducible.  It is validated by (i) finite differences of
 its own autograd gradients, (ii) an independent NumPy restatement of the
-forward pass (``oracle/numpy_check.py``) and (iii) closed-form identities -- see
+path in restructured algebra with a hand-derived reverse mode (``oracle/kernel_math.py``) and (iii) closed-form identities -- see
 ``tests/test_oracle.py``.  It has never been compared with TensorFlow output.
 
 All arithmetic is float64 (the reference default, cbfssm/model/base_model.py:8)
