@@ -368,10 +368,14 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (0 = workload default)")
     ap.add_argument("--workload", default="robomove_m20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--M", type=int, default=0, help="override the workload's number of inducing points (kernel-path studies)")
     ap.add_argument("--flags", type=int, default=0, help="cbf_shape.flags (1 cooperative kernels, 2 no tensor cores)")
     args = ap.parse_args()
     WORK.clear()
     WORK.update(WORKLOADS[args.workload])
+    if args.M > 0:
+        WORK["M"] = args.M
+        WORK["name"] += " [M overridden to %d]" % args.M
     if args.batch <= 0:
         args.batch = WORK["batch"]
     if args.impl == "reference":

@@ -80,6 +80,10 @@ constexpr size_t kMaxSmem = 227 * 1024;
 // 50-3 200 particles, tools/bench_cross.sh), so the cooperative kernels serve only M without a specialised path.
 constexpr int kMinParticlesRegisterPath = 1;
 constexpr int kMinParticlesTensorPath = 1;
+#ifndef CBF_MIN_TENSOR_M
+#define CBF_MIN_TENSOR_M 16
+#endif
+constexpr int kMinTensorM = CBF_MIN_TENSOR_M;   // smallest M served by the tensor path
 
 // Live chain segments of both backward-message runs (cbfssm.py:123-136, SURVEY 8a note 5).
 static std::vector<Chain> build_chains(int T, int R) {
@@ -117,7 +121,7 @@ struct Plan {
   const DimOps *ops;
   bool half;                     // CBFSSMHALF: no backward-message GP, x_0 supplied by the caller
   size_t off_x0b;
-  // tensor-core path (48 <= M <= 128, enough particles)
+  // tensor-core path (16 <= M <= 128, enough particles)
   bool tc_fwd, tc_rev;
   size_t colsf, colsb;           // columns (live steps x particles) of the operand matrices
   size_t off_rpart;              // per-CTA float64 partials of the tcgen05 outer-product kernel
@@ -212,7 +216,7 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   p.off_x0b = o; o = align_up(o + sizeof(float) * p.dx * np, 256);
   // ---- tensor-core path ----
   p.tc_fwd = p.tc_rev = false;
-  if (p.ops && p.ops->fw_forward_tc != nullptr && s->M >= 48 && s->M <= 128 &&
+  if (p.ops && p.ops->fw_forward_tc != nullptr && s->M >= kMinTensorM && s->M <= 128 &&
       !(s->flags & (CBF_FLAG_FORCE_COOPERATIVE | CBF_FLAG_NO_TENSOR_CORES)) &&
       ((s->flags & CBF_FLAG_FORCE_TENSOR_CORES) || s->n_local >= kMinParticlesTensorPath)) {
     p.tc_fwd = p.ops->smem_tc(s->M, 0) <= kMaxSmem && p.ops->smem_tc(s->M, 1) <= kMaxSmem;
@@ -778,7 +782,9 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
       CBF_CUDA(tc_outer(mf, p.D.M, p.dx, p.din, rpart, rdf, wi > 0, st));
     }
     // message GP: round r runs the r-th piece of every live chain (ascending time; the message adjoint crosses
-    // pieces through the carry buffer)
+    // pieces through the carry buffer).  Without a message GP (CBFSSMHALF) its scalar sums are zero.
+    if (p.rounds_b.empty())
+      CBF_CUDA(cudaMemsetAsync(ws.acc_b + p.Lb.scal_off(), 0, sizeof(double) * (size_t)p.nsc_b, st));
     for (size_t ri = 0; ri < p.rounds_b.size(); ++ri) {
       const std::vector<Chain> &round = p.rounds_b[ri];
       int cols = 0;

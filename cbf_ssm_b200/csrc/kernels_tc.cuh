@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05 / TMEM) forward rollout kernels for large M (48 <= M <= 128).
+// Tensor-core (tcgen05 / TMEM) forward rollout kernels for large M (16 <= M <= 128).
 //
 // For a CTA tile of 128 particles the M x M contraction a = P k of every time step is a real
 // GEMM, D[128 x MP] = K[128 x MP] . P[MP x MP], and runs on the 5th-generation tensor cores:

@@ -14,6 +14,7 @@ PyTorch is used for device memory, streams and ``torch.distributed`` only.
 from __future__ import annotations
 
 import contextlib
+import os
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, Optional
@@ -232,6 +233,8 @@ class ElboEngine:
             nbytes = C.c_size_t(0)
             check(self.lib.cbf_workspace_bytes(C.byref(shape), C.byref(nbytes)))
             self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            if os.environ.get("CBFSSM_B200_POISON_WS"):     # test aid: every byte 0xFF = NaN in float32 / float64,
+                self._ws.fill_(0xFF)                        # so a read of never-written workspace cannot go unnoticed
             gl = cbf_grad_layout()
             check(self.lib.cbf_grad_layout_get(C.byref(shape), C.byref(gl)))
             self._gl = gl

@@ -61,9 +61,9 @@ typedef struct cbf_shape {
 /* Use the cooperative shared-memory kernels even when a register-resident
  * instantiation for this (dims, M) is compiled in (parity tests cover both). */
 #define CBF_FLAG_FORCE_COOPERATIVE 1
-/* Do not use the tcgen05 tensor-core forward kernels (selected by default for 48 <= M <= 128). */
+/* Do not use the tcgen05 tensor-core forward kernels (selected by default for 16 <= M <= 128). */
 #define CBF_FLAG_NO_TENSOR_CORES 2
-/* The register-resident kernels (compiled-in small M) and the tensor-core kernels (48 <= M <= 128) are the
+/* The register-resident kernels (compiled-in small M) and the tensor-core kernels (16 <= M <= 128) are the
  * default at every particle count; the cooperative kernels serve every other M.  These flags select a
  * specialised path explicitly (they fail if it does not exist for the shape). */
 #define CBF_FLAG_FORCE_REGISTER 4
