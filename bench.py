@@ -369,13 +369,18 @@ def main():
     ap.add_argument("--workload", default="robomove_m20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--M", type=int, default=0, help="override the workload's number of inducing points (kernel-path studies)")
+    ap.add_argument("--S", type=int, default=0, help="override the particles per sequence")
+    ap.add_argument("--T", type=int, default=0, help="override the sequence length")
+    ap.add_argument("--R", type=int, default=0, help="override recog_len")
     ap.add_argument("--flags", type=int, default=0, help="cbf_shape.flags (1 cooperative kernels, 2 no tensor cores)")
     args = ap.parse_args()
     WORK.clear()
     WORK.update(WORKLOADS[args.workload])
-    if args.M > 0:
-        WORK["M"] = args.M
-        WORK["name"] += " [M overridden to %d]" % args.M
+    for key in ("M", "S", "T", "R"):
+        v = getattr(args, key)
+        if v > 0:
+            WORK[key] = v
+            WORK["name"] += " [%s overridden to %d]" % (key, v)
     if args.batch <= 0:
         args.batch = WORK["batch"]
     if args.impl == "reference":

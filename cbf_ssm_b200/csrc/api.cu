@@ -245,22 +245,37 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
       size_t bytes_win = mats_bytes((size_t)wf * s->n_local, s->M, p.dx, p.din);
       p.rounds_b.clear();
       if (!p.half) {
-        const size_t nchains = p.chains.size();
-        size_t wb = budget / (col_b * (size_t)s->n_local * nchains);
-        if (wb < 1) wb = 1;
-        if (wb * nchains * (size_t)s->n_local >= ((size_t)1 << 31)) wb = (((size_t)1 << 31) - 1) / ((size_t)s->n_local * nchains);
-        if (wb < 1) { set_error("too many particles for one time step of operand tiles"); return CBF_ERR_INVALID_SHAPE; }
+        // Pack whole chains into launches of at most `cap` columns (chain-steps x particles within the budget);
+        // a chain is cut only where it does not fit, and its pieces go to successive launches in ascending
+        // time so that the message adjoint can cross them through the carry buffer.
+        size_t cap = budget / (col_b * (size_t)s->n_local);
+        if (cap < 1) cap = 1;
+        if (cap * (size_t)s->n_local >= ((size_t)1 << 31)) cap = (((size_t)1 << 31) - 1) / s->n_local;
+        if (cap < 1) { set_error("too many particles for one time step of operand tiles"); return CBF_ERR_INVALID_SHAPE; }
+        std::vector<Chain> cur;
+        size_t cur_cols = 0;
         for (const Chain &c : p.chains) {
-          const int len = c.t_hi - c.t_lo + 1, npieces = (int)((len + wb - 1) / wb), plen = ceil_div(len, npieces);
-          for (int k = 0; k < npieces; ++k) {
+          int lo = c.t_lo;
+          bool first = true, in_cur = false;
+          while (lo <= c.t_hi) {
+            if (cur_cols >= cap || in_cur || (int)cur.size() >= kMaxChains) {   // launch full, or it holds this chain's previous piece
+              p.rounds_b.push_back(cur);
+              cur.clear(); cur_cols = 0; in_cur = false;
+            }
+            const size_t space = cap - cur_cols, left = (size_t)(c.t_hi - lo + 1);
+            const int take = (int)(left < space ? left : space);
             Chain piece = c;
-            piece.t_lo = c.t_lo + k * plen;
-            piece.t_hi = piece.t_lo + plen - 1 < c.t_hi ? piece.t_lo + plen - 1 : c.t_hi;
-            piece.carry = (k > 0 ? 1 : 0) | (k + 1 < npieces ? 2 : 0);
-            if ((int)p.rounds_b.size() <= k) p.rounds_b.emplace_back();
-            p.rounds_b[k].push_back(piece);
+            piece.t_lo = lo;
+            piece.t_hi = lo + take - 1;
+            piece.carry = (first ? 0 : 1) | (piece.t_hi < c.t_hi ? 2 : 0);
+            cur.push_back(piece);
+            cur_cols += (size_t)take;
+            in_cur = piece.t_hi < c.t_hi;   // the next piece of this chain must wait for this launch
+            lo += take;
+            first = false;
           }
         }
+        if (!cur.empty()) p.rounds_b.push_back(cur);
         for (auto &round : p.rounds_b) {
           int col = 0;
           for (Chain &c : round) { c.col0 = col; col += c.t_hi - c.t_lo + 1; }
