@@ -211,3 +211,21 @@ def test_unicycle_generator_obeys_its_kinematics():
     assert np.allclose(rob.pos, start, atol=1e-12) and rob.angle == pytest.approx(0.0, abs=1e-12)
     rob.propagate([np.pi / 2, 1.0])                              # quarter turn to the right
     assert np.allclose(rob.pos - start, [1.0, 1.0]) and rob.angle == pytest.approx(np.pi / 2)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU restatement on the host cores) prints one JSON line with the keys the
+    driver reads; runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "particle-steps/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["vs_baseline"] is None and line["gpu_launches"] == 0
