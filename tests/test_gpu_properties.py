@@ -260,3 +260,25 @@ def test_outputs_writes_the_reference_report_files(tmp_path):
     block = dump.split("IP pos f:\n")[1].split("\n\n")[0].strip().split("\n")
     assert len(block) == 20 and len(block[0].split()) == dim_x + 1      # [M, dx + du] rows
     assert np.loadtxt(os.path.join(out_dir, "training_loss.txt")).shape == (2, 3)
+
+
+def test_bench_b200_arm_prints_the_contract_line():
+    """bench.py on the GPU (small batch): one JSON line with the contract keys, roofline and end-to-end objects."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--batch", "64",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["scaling"] == "weak" and line["value"] > 0 and line["gpu_launches"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 64 * 300 * 4 * 4 and line["e2e"]["d2h_bytes_per_step"] == 8
+    assert 0 < line["e2e"]["value"] <= line["value"] * 1.05
+    r = line["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"):
+        assert key in r, key
+    assert 0 < r["frac"] < 1 and r["unit"] == "TFLOP/s"
+    assert "workload" in line["config"] and "model" not in line["config"]
