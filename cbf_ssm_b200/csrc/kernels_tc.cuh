@@ -31,6 +31,10 @@
 namespace cbf {
 
 constexpr int kTcThreads = 128;   // threads (= particles = TMEM lanes) of one particle tile
+#ifndef CBF_TC_CHUNK_UNROLL
+#define CBF_TC_CHUNK_UNROLL 1
+#endif
+constexpr int kTcChunkUnroll = CBF_TC_CHUNK_UNROLL;   // unroll of the 16-row chunk loops when M is a compile-time constant
 
 // Barrier over the 128 threads of one particle tile (named barrier 1 + tile; 0 is __syncthreads).
 __device__ __forceinline__ void tile_sync(int tile) {
@@ -468,7 +472,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
   uint32_t ra[16];
   tmem_ld16_issue(trow, ra);
-#pragma unroll(MC ? 1 : 1)
+#pragma unroll(MC ? kTcChunkUnroll : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16], kp[16];
     tc_read_row16(c.K1, c.K2, t, cc, kp);
@@ -540,7 +544,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   // ---- b'' = a' (S gv) 2^-e -> fp16 split rows of B ----
   uint32_t ra1[16];
   tmem_ld16_issue(trow1, ra1);
-#pragma unroll(MC ? 1 : 1)
+#pragma unroll(MC ? kTcChunkUnroll : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float a[16];
     tmem_ld_wait(ra1);
@@ -586,7 +590,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   for (int j = 0; j < J2; ++j) { x2[j] = pack2(xt[2 * j], xt[2 * j + 1]); L2[j] = 0ull; }
 #pragma unroll
   for (int j = 0; j < N2; ++j) xs2[j] = 0ull;
-#pragma unroll(MC ? 1 : 1)
+#pragma unroll(MC ? kTcChunkUnroll : 1)
   for (int cc = 0; cc < MP / 16; ++cc) {
     float pb[16], a[16], kp[16], bb[16];
     {
