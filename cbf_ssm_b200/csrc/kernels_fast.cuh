@@ -63,6 +63,9 @@ constexpr TileCfg pick_tiles(int M, int Din, int Dout) {
   double best_cost = 1e30;
   for (int tr = 2; tr <= 8; ++tr)
     for (int tc = 2; tc <= 6; tc += 4) {
+#ifdef CBF_FORCE_TC6
+      if (tc != 6) continue;
+#endif
       const int rg = cdiv(M, tr), cg = cdiv(M, tc) + 2 * cdiv(Dout, tc) + cdiv(Din + 1, tc);
       const int rounds = cdiv(rg * cg, 32);
       if (rounds * tr * tc > 60) continue;   // accumulator registers per lane
