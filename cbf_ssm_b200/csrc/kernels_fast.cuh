@@ -441,8 +441,43 @@ struct WarpAcc {
     }
   }
 
+  // With CG dividing 32 a lane's tiles of all rounds (tile = lane + 32 r) lie in the same column group, so the
+  // right-operand loads are shared by the rounds (M=20 message GP: 14 -> 12 LDS.128 per 4 particles).
+  static constexpr bool kSharedRight = ROUNDS > 1 && (32 % CG == 0);
+
   // stg holds this step's vectors of the warp's 32 particles (all lanes have written + __syncwarp).
   __device__ __forceinline__ void accumulate(const float *__restrict__ stg) {
+    if constexpr (kSharedRight) {
+      const float *rp = stg + roff[0];
+#pragma unroll(kAccUnroll)
+      for (int n4 = 0; n4 < 32; n4 += 4) {
+        float4 r0[TC2], r1[TC2];
+#pragma unroll
+        for (int j = 0; j < TC2; ++j) {
+          r0[j] = *reinterpret_cast<const float4 *>(rp + j * kPS + 2 * n4);
+          r1[j] = *reinterpret_cast<const float4 *>(rp + j * kPS + 2 * n4 + 4);
+        }
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+          const float *lp = stg + loff[r];
+          float4 l[TR];
+#pragma unroll
+          for (int i = 0; i < TR; ++i) l[i] = *reinterpret_cast<const float4 *>(lp + i * kSLD + n4);
+#pragma unroll
+          for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int j = 0; j < TC2; ++j) {
+              unsigned long long c = acc[r][i][j];
+              c = ffma2_bcast(r0[j].x, r0[j].y, l[i].x, c);
+              c = ffma2_bcast(r0[j].z, r0[j].w, l[i].y, c);
+              c = ffma2_bcast(r1[j].x, r1[j].y, l[i].z, c);
+              c = ffma2_bcast(r1[j].z, r1[j].w, l[i].w, c);
+              acc[r][i][j] = c;
+            }
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
       const float *lp = stg + loff[r], *rp = stg + roff[r];
