@@ -173,13 +173,13 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
     set_error("dims (dx=%d,du=%d,dy=%d) are not compiled in (see csrc/dims_list.h)", s->dx, s->du, s->dy);
     return CBF_ERR_UNSUPPORTED_DIMS;
   }
+  // The cooperative kernels keep P, the [m][n] vectors and the accumulators in shared memory (M <= ~110); above
+  // that only the tensor path can run the shape (checked once it has been selected below).
+  bool coop_fits = true;
+  size_t coop_need = 0;
   if (p.ops) {
     for (int w = 0; w < 4; ++w)
-      if (p.ops->smem_bytes(s->M, w) > kMaxSmem) {
-        set_error("M=%d: resident parameter set needs %zu B of shared memory (> %zu)", s->M,
-                  p.ops->smem_bytes(s->M, w), kMaxSmem);
-        return CBF_ERR_UNSUPPORTED_M;
-      }
+      if (p.ops->smem_bytes(s->M, w) > kMaxSmem) { coop_fits = false; coop_need = p.ops->smem_bytes(s->M, w); }
   }
   Dims &D = p.D;
   D.B = s->B; D.S = s->S; D.T = s->T; D.M = s->M; D.R = s->R; D.condition = s->condition ? 1 : 0;
@@ -297,6 +297,11 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
       p.off_carry_f = o; o = align_up(o + sizeof(float) * p.dx * np, 256);
       p.off_carry_b = o; o = align_up(o + sizeof(float) * (p.chains.size() + 1) * p.dh * np, 256);
     }
+  }
+  if (!coop_fits && !(p.tc_fwd && p.tc_rev)) {
+    set_error("M=%d: resident parameter set needs %zu B of shared memory (> %zu) and the tensor path (16 <= M <= 128) "
+              "is not available for this call", s->M, coop_need, kMaxSmem);
+    return CBF_ERR_UNSUPPORTED_M;
   }
   p.total = o;
   return 0;
@@ -664,8 +669,15 @@ CBF_API const char *cbf_last_error_string(void) { return g_err; }
 CBF_API int cbf_supported(int32_t M, int32_t dx, int32_t du, int32_t dy) {
   const DimOps *ops = find_ops(dx, du, dy, M, true);
   if (!ops || M < 1) return 0;
+  bool coop_fits = true;
   for (int w = 0; w < 4; ++w)
-    if (ops->smem_bytes(M, w) > kMaxSmem) return 0;
+    if (ops->smem_bytes(M, w) > kMaxSmem) coop_fits = false;
+  if (!coop_fits) {   // only the tensor path can take it
+    if (ops->fw_forward_tc == nullptr || ops->fw_reverse_tc == nullptr || M < kMinTensorM || M > 128) return 0;
+    for (int w = 0; w < 4; ++w)
+      if (ops->smem_tc(M, w) > kMaxSmem) return 0;
+    return 1;
+  }
   return ops->fixed_M ? 2 : 1;
 }
 

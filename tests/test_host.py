@@ -42,6 +42,8 @@ def test_host_only_entry_points_without_gpu(lib):
     assert lib.cbf_supported(100, 14, 7, 7) == 1
     assert lib.cbf_supported(20, 5, 5, 5) == 0          # dims not compiled in
     assert lib.cbf_supported(500, 4, 2, 2) == 0         # resident set exceeds one SM
+    assert lib.cbf_supported(128, 4, 2, 2) == 1         # too large for the cooperative kernels: tensor path only
+    assert lib.cbf_supported(128, 14, 7, 7) == 1 and lib.cbf_supported(129, 4, 2, 2) == 0
     n = C.c_size_t(0)
     s = _shape()
     assert lib.cbf_workspace_bytes(C.byref(s), C.byref(n)) == 0 and n.value > 0
