@@ -4,15 +4,23 @@ This file is the checker, not the product: only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it.  Nothing under ``cbf_ssm_b200/`` does.
 
-PARITY UNPINNED.  The reference (silvanmelchior/CBF-SSM) builds a TensorFlow 1.8
-graph; TensorFlow cannot be imported in this image (Python 3.12, no network),
-and the reference ships no tests, golden vectors or seeds.  This oracle is
-therefore a float64 op-for-op *restatement* of the reference files cited on each
-function, with every ``tf.random_normal`` draw turned into an explicit input so
-that results are reproducible.  It is validated by (i) finite differences of
-its own autograd gradients, (ii) an independent NumPy restatement of the
-path in restructured algebra with a hand-derived reverse mode (``oracle/kernel_math.py``) and (iii) closed-form identities -- see
-``tests/test_oracle.py``.  It has never been compared with TensorFlow output.
+PARITY PINNED BY EXECUTING THE REFERENCE'S SOURCE.  The reference (silvanmelchior/CBF-SSM)
+builds a TensorFlow 1.8 graph; TensorFlow cannot be imported in this image (Python 3.12,
+no network) and the reference ships no tests, golden vectors or seeds.  This oracle is a
+float64 op-for-op *restatement* of the reference files cited on each function, with every
+``tf.random_normal`` draw turned into an explicit input.  It is pinned by
+``tests/golden/ref_*.npz``: fixtures written by ``oracle/run_reference.py``, which imports the
+reference's UNMODIFIED ``cbfssm/model/{tf_transform,gp_tf,base_model,cbfssm,cbfssmhalf}.py``
+from the checkout and executes them under ``oracle/tf_shim`` (an eager float64 stand-in for
+the ~60 TensorFlow symbols they use).  ``tests/test_oracle.py`` asserts this restatement
+reproduces those fixtures to 1e-10 (loss terms, all 12 gradients, states, moments, first Adam
+step, and the resample schedule the reference's own ``tf.cond`` predicates took) on the six
+named configurations and four harder cases.  What remains restated rather than executed is
+TensorFlow's *library* behaviour (softplus, cholesky, triangular solve,
+MVN log-prob / KL formulas, moments, Adam), written out in the shim; it has not been compared
+with a TensorFlow binary.  Further checks: finite differences of the autograd gradients, an
+independent NumPy restatement in restructured algebra (``oracle/kernel_math.py``) and closed
+forms.
 
 All arithmetic is float64 (the reference default, cbfssm/model/base_model.py:8)
 on PyTorch-CPU so that autograd supplies the reference gradients

@@ -1,7 +1,9 @@
 """CPU oracle for ``CBFSSMHALF`` (cbfssm/model/cbfssmhalf.py).  TEST INFRASTRUCTURE ONLY.
 
 Same status as ``cbfssm_oracle.py``: a float64 PyTorch-CPU restatement of the TensorFlow-1.8 graph with
-injected normal draws; PARITY UNPINNED (TensorFlow cannot run here, the reference ships no vectors).
+injected normal draws, pinned by fixtures from the reference's unmodified ``cbfssmhalf.py`` executed under
+``oracle/tf_shim`` (``tests/golden/ref_half_*.npz``; the GRU cell / dense layer are TF library code restated
+in the shim).
 CBFSSMHALF has no backward-message GP: x_0 comes from a recognition model (zero-padded first output,
 or a GRU(16)+dense over the reversed first ``recog_len`` steps, cbfssmhalf.py:64-95) and the forward
 step conditions only the first ``dim_y`` state dimensions (cbfssmhalf.py:144-156); ``var_y`` has

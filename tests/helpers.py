@@ -34,6 +34,16 @@ def rel_inf(a, b):
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
 
 
+def elementwise_ok(a, b, tol, floor=1e-3):
+    """Every entry: |a - b| <= tol * max(|b|, floor * max|b|).  ``rel_inf`` alone leaves entries far below a
+    tensor's maximum unchecked; this bounds each one relative to itself, down to ``floor`` of the maximum
+    (below that the float32 path carries no significant digits relative to the entry)."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    scale = np.maximum(np.abs(b), floor * np.max(np.abs(b)) + 1e-300)
+    return bool(np.all(np.abs(a - b) <= tol * scale))
+
+
 # Named configurations of SURVEY.md 8(d) at the reference's own batch sizes
 # (cfg4 / cfg5 with the particle count reduced so the oracle finishes in seconds).
 NAMED_CASES = {
@@ -61,3 +71,45 @@ def named_case(name):
     cfg, params, u, y, eps_b, z_b, eps_f = make_problem(c["dx"], c["du"], c["dy"], c["M"], c["S"], c["B"], c["T"],
                                                         c["R"], c["kap"], c["lf"], seed=c["seed"], **c["over"])
     return cfg, params, u, y, eps_b, z_b, eps_f, c.get("cond", True)
+
+
+# Harder cases ("strong": every gradient path carries weight; entropy factor on) that also get a
+# fixture from the reference's own source (tests/golden/make_golden.py).
+STRONG_REF_CASES = {
+    # name: (dx, du, dy, M, S, B, T, R, kap, lf, seed, condition)
+    "strong_m20": (4, 2, 2, 20, 16, 4, 24, 6, 1.0, (20.0, 0.1), 11, True),
+    "strong_m100": (4, 2, 2, 100, 16, 8, 40, 10, 1.0, (10.0, 0.3), 12, True),
+    "strong_m7_free_run": (4, 2, 2, 7, 5, 3, 17, 4, 3.0, (5.0, 0.2), 13, False),
+    "strong_sarcos_dims_m33": (14, 7, 7, 33, 6, 2, 20, 4, 50.0, (6.0, 0.1), 14, True),
+}
+
+
+def strong_ref_case(name):
+    dx, du, dy, M, S, B, T, R, kap, lf, seed, cond = STRONG_REF_CASES[name]
+    return make_problem(dx, du, dy, M, S, B, T, R, kap, lf, seed=seed, strong=True) + (cond,)
+
+
+HALF_REF_CASES = {
+    # name: (dx, du, dy, M, S, B, T, R, kap, seed, condition, recog_model)
+    "half_rnn_m20": (4, 2, 2, 20, 8, 3, 30, 8, 2.0, 5, True, "rnn"),
+    "half_output_m20_free_run": (4, 1, 1, 20, 8, 3, 25, 5, 10.0, 6, False, "output"),
+    "half_rnn_m100": (4, 1, 1, 100, 10, 2, 20, 6, 1.0, 7, True, "rnn"),
+}
+
+
+def half_ref_case(name):
+    """CBFSSMHALF problem incl. GRU(16)+dense recognition weights (TF creation order)."""
+    from oracle import cbfssmhalf_oracle as H
+    dx, du, dy, M, S, B, T, R, kap, seed, cond, recog = HALF_REF_CASES[name]
+    cfg, _, u, y, _, _, eps_f = make_problem(dx, du, dy, M, S, B, T, R, kap, (10.0, 0.0), seed=seed, strong=True)
+    params = H.init_params_half(cfg, seed)
+    g = np.random.default_rng(seed + 3000)
+    nh, din = 16, du + dy
+
+    def glorot(shape):
+        lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+        return g.uniform(-lim, lim, shape)
+    w = dict(gates_kernel=glorot((din + nh, 2 * nh)), gates_bias=np.ones(2 * nh) + 0.1 * g.standard_normal(2 * nh),
+             candidate_kernel=glorot((din + nh, nh)), candidate_bias=0.1 * g.standard_normal(nh),
+             dense_kernel=glorot((nh, dx)), dense_bias=0.1 * g.standard_normal(dx))
+    return cfg, params, w, u, y, eps_f, cond, recog
