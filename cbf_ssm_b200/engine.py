@@ -228,19 +228,24 @@ class ElboEngine:
                          int(self.flags) | (32 if d.half else 0))
 
     def _ensure_workspace(self, shape):
-        key = (shape.B, shape.T, shape.n_local)
-        if self._ws_key != key:
-            nbytes = C.c_size_t(0)
-            check(self.lib.cbf_workspace_bytes(C.byref(shape), C.byref(nbytes)))
+        # The plan the library binds onto the buffer depends on everything in ``shape`` (flags select the kernel
+        # path and with it extra sections) and on the tensor path's window budget, so the size is asked for on
+        # every call (a host-side computation) and the buffer grows whenever the answer exceeds it.
+        nbytes = C.c_size_t(0)
+        check(self.lib.cbf_workspace_bytes(C.byref(shape), C.byref(nbytes)))
+        key = (shape.B, shape.T, shape.n_local, int(shape.flags))
+        if self._ws is None or nbytes.value > self._ws.numel():
             self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
             if os.environ.get("CBFSSM_B200_POISON_WS"):     # test aid: every byte 0xFF = NaN in float32 / float64,
                 self._ws.fill_(0xFF)                        # so a read of never-written workspace cannot go unnoticed
+        if self._ws_key != key:
             gl = cbf_grad_layout()
             check(self.lib.cbf_grad_layout_get(C.byref(shape), C.byref(gl)))
             self._gl = gl
             # flat kernel-level gradient, followed by the three ELBO terms so that one
             # all-reduce covers both
-            self._gflat = torch.zeros(gl.total + 4, dtype=F64, device=self.device)
+            if self._gflat is None or self._gflat.numel() != gl.total + 4:
+                self._gflat = torch.zeros(gl.total + 4, dtype=F64, device=self.device)
             self._ws_key = key
 
     def prologue(self):

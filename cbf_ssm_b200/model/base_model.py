@@ -116,9 +116,23 @@ class BaseModel:
                     nxt += 1
                 else:
                     window.pop(j)
+        order = self._same_order_on_every_rank(order)
         self._ds = (data_in, data_out)
         self._order = order
         self._cursor = 0
+
+    def _same_order_on_every_rank(self, order):
+        """With a process group every rank shards the *same* minibatch, so the shuffled order is
+        rank 0's, broadcast -- the default shuffle RNG is unseeded like the reference's."""
+        group = getattr(self, "_group", None)
+        if group is None or getattr(self, "world", 1) <= 1:
+            return order
+        import torch
+        import torch.distributed as dist
+        dev = self.engine.device if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.as_tensor(np.ascontiguousarray(order, dtype=np.int64)).to(dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0), group=group)
+        return t.cpu().numpy()
 
     def _next_batch(self):
         if self._ds is None or self._cursor >= self._order.size:

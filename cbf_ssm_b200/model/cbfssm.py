@@ -16,6 +16,8 @@ contiguously over the ranks.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -26,25 +28,25 @@ _PRED = ("pred_mean", "pred_var", "internal_mean", "internal_var", "mse", "sde",
 
 
 class Saver:
-    """tf.train.Saver look-alike: parameters + Adam slots (cbfssm.py:276; trainer.py:31,59,63)."""
+    """tf.train.Saver look-alike (cbfssm.py:276; trainer.py:31,59,63): like the reference's, it persists
+    *every* variable of the model -- whatever ``model.state_dict()`` returns (the 12 tensors and their Adam
+    slots; CBFSSMHALF adds its recognition network and that network's Adam slots)."""
 
     def __init__(self, model):
         self.model = model
 
     def save(self, sess, path):
-        eng = self.model.engine
-        if self.model.rank == 0:
-            torch.save({"theta": eng.theta.cpu(), "adam_m": eng.adam_m.cpu(), "adam_v": eng.adam_v.cpu(),
-                        "adam_t": eng.adam_t, "names": eng.names}, path)
+        model = self.model
+        if model.rank == 0:
+            tmp = path + ".tmp"
+            torch.save(model.state_dict(), tmp)
+            os.replace(tmp, path)
+        if model.world > 1:      # nobody restores before rank 0 has finished writing
+            torch.distributed.barrier(group=model._group)
         return path
 
     def restore(self, sess, path):
-        eng = self.model.engine
-        ck = torch.load(path, map_location="cpu")
-        eng.theta.copy_(ck["theta"])
-        eng.adam_m.copy_(ck["adam_m"])
-        eng.adam_v.copy_(ck["adam_v"])
-        eng.adam_t = int(ck["adam_t"])
+        self.model.load_state_dict(torch.load(path, map_location="cpu"))
 
 
 class CBFSSM(BaseModel):
@@ -88,6 +90,22 @@ class CBFSSM(BaseModel):
         eng.adam_m.zero_()
         eng.adam_v.zero_()
         eng.adam_t = 0
+
+    def state_dict(self):
+        """Everything a checkpoint must hold: parameters and optimiser state (tf.train.Saver saves all global
+        variables, Adam slots included)."""
+        eng = self.engine
+        return {"theta": eng.theta.cpu(), "adam_m": eng.adam_m.cpu(), "adam_v": eng.adam_v.cpu(),
+                "adam_t": eng.adam_t, "names": eng.names}
+
+    def load_state_dict(self, ck):
+        eng = self.engine
+        if tuple(ck["names"]) != tuple(eng.names) or ck["theta"].numel() != eng.theta.numel():
+            raise ValueError("checkpoint was written by a model with different variables")
+        eng.theta.copy_(ck["theta"])
+        eng.adam_m.copy_(ck["adam_m"])
+        eng.adam_v.copy_(ck["adam_v"])
+        eng.adam_t = int(ck["adam_t"])
 
     def inject_draws(self, eps_b, z_b, eps_f):
         """Use these N(0,1) draws ([2,T,B,S], [2,T,B,S], [T-1,B,S]) for the next minibatch."""
@@ -143,8 +161,10 @@ class CBFSSM(BaseModel):
             ud = u.to(dev, non_blocking=True)
             yd = y.to(dev, non_blocking=True)
         n0, nl = self._shard(B)
-        if nl < 1:
-            raise ValueError("minibatch has fewer particles than ranks")
+        # decided from (N, world) alone, so every rank raises together instead of some entering the all-reduce
+        per = -(-(B * d.samples) // self.world)
+        if per * (self.world - 1) >= B * d.samples:
+            raise ValueError("minibatch has too few particles for this many ranks")
         eb, zb, ef = self._draws(B, T, n0, nl)
         main.wait_stream(self._copy_stream)
         ud.record_stream(main)

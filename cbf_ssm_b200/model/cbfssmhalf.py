@@ -98,6 +98,21 @@ class CBFSSMHALF(CBFSSM):
                 v.fill_(1.0 if k == "gates_bias" else 0.0)
         self.phi_m.zero_(); self.phi_v.zero_()
 
+    def state_dict(self):
+        """The GP / noise variables plus the recognition network and its Adam slots (the reference's Saver keeps
+        the GRU and dense-layer variables, cbfssmhalf.py:85-91, like any other global variable)."""
+        ck = super().state_dict()
+        ck.update(recog_model=self.recog, phi=self.phi.cpu(), phi_m=self.phi_m.cpu(), phi_v=self.phi_v.cpu())
+        return ck
+
+    def load_state_dict(self, ck):
+        if ck.get("recog_model") != self.recog or ck["phi"].numel() != self.phi.numel():
+            raise ValueError("checkpoint was written with a different recognition model")
+        super().load_state_dict(ck)
+        self.phi.copy_(ck["phi"])
+        self.phi_m.copy_(ck["phi_m"])
+        self.phi_v.copy_(ck["phi_v"])
+
     def inject_draws(self, eps_f):
         """Use these N(0,1) draws [T-1, B, S] for the next minibatch."""
         self._injected = np.asarray(eps_f)

@@ -15,10 +15,12 @@ from tests.helpers import make_problem
 
 
 def _partition(N, world, rank):
-    # same arithmetic as cbf_ssm_b200.model.cbfssm.CBFSSM._shard
-    per = -(-N // world)
-    n0 = min(rank * per, N)
-    return n0, min(n0 + per, N) - n0
+    """The product's own partition function (cbf_ssm_b200.model.cbfssm.CBFSSM._shard) called on a stand-in
+    object: the model class cannot be constructed without a GPU, the method itself is plain arithmetic."""
+    from types import SimpleNamespace
+    from cbf_ssm_b200.model.cbfssm import CBFSSM
+    stub = SimpleNamespace(dims=SimpleNamespace(samples=1), world=world, rank=rank)
+    return CBFSSM._shard(stub, N)
 
 
 def _flat(kl):
@@ -53,8 +55,15 @@ def _worker(rank, world, port, out_dir):
     vec = np.concatenate((_flat(out["kernel_level"]), [out["loglik"], out["kl_x"], out["entropy"]]))
     t = torch.tensor(vec)
     dist.all_reduce(t)                                             # the one collective of a step
+    # every rank must shard the same minibatch: the product's load_ds broadcasts rank 0's shuffled order
+    from types import SimpleNamespace
+    from cbf_ssm_b200.model.base_model import BaseModel
+    stub = SimpleNamespace(_group=dist.group.WORLD, world=world, engine=SimpleNamespace(device="cpu"))
+    mine = np.random.RandomState(100 + rank).permutation(37)        # ranks disagree before the broadcast
+    agreed = BaseModel._same_order_on_every_rank(stub, mine)
     if rank == 0:
         np.save(os.path.join(out_dir, "reduced.npy"), t.numpy())
+    np.save(os.path.join(out_dir, f"order{rank}.npy"), agreed)
     dist.destroy_process_group()
 
 
@@ -66,6 +75,8 @@ def test_two_rank_shards_all_reduce_to_the_unsharded_result(tmp_path):
     out, _ = KM.elbo_value_and_grad(cfg, {k: v.numpy() for k, v in params.items()}, u, y, eb, zb, ef, True)
     ref = np.concatenate((_flat(out["kernel_level"]), [out["loglik"], out["kl_x"], out["entropy"]]))
     assert np.allclose(red, ref, rtol=1e-10, atol=1e-12)
+    o0, o1 = np.load(tmp_path / "order0.npy"), np.load(tmp_path / "order1.npy")
+    assert np.array_equal(o0, o1) and np.array_equal(o0, np.random.RandomState(100).permutation(37))
 
 
 @pytest.mark.parametrize("N,world", [(1600, 8), (100, 8), (7, 4), (3, 8)])

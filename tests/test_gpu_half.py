@@ -111,3 +111,44 @@ def test_half_model_rnn_recognition_and_training(tmp_path):
     model.load_ds(sess, ds.test_in_batch[:1], ds.test_out_batch[:1])
     pm, pv = sess.run((model.pred_mean, model.pred_var), {model.condition: False})
     assert pm.shape == (1, 30, 1) and np.all(pv > 0)
+
+
+def test_half_checkpoint_round_trip_restores_the_recognition_network(tmp_path):
+    """Saver.save -> fresh model (different initial values) -> Saver.restore gives identical predictions and an
+    identical next training step: the GRU / dense weights and their Adam slots are part of the checkpoint, like
+    every global variable of the reference's tf.train.Saver (cbfssmhalf.py:85-91,199)."""
+    from cbf_ssm_b200.datasets import SpringNonlinearSynthetic
+    from cbf_ssm_b200.model import CBFSSMHALF, Session
+
+    class SmallSpring(SpringNonlinearSynthetic):
+        exp_len = 300
+    ds = SmallSpring(20, 10, seed=2)
+    dim_x = 4
+    config = {'ds': SmallSpring, 'batch_size': 4, 'shuffle': 1, 'dim_x': dim_x, 'ind_pnt_num': 20, 'samples': 8,
+              'learning_rate': 0.01, 'loss_factors': np.asarray([10., 0.]), 'k_factor': 1., 'recog_len': 6,
+              'zeta_pos': 2., 'zeta_mean': 0.1 ** 2, 'zeta_var': 0.01 ** 2, 'var_x': np.asarray([0.1 ** 2] * dim_x),
+              'var_y': np.asarray([1. ** 2] * SmallSpring.dim_y), 'gp_var': 0.1 ** 2, 'gp_len': 1.}
+    u, y = ds.train_in_batch[:4], ds.train_out_batch[:4]
+    T = u.shape[1]
+    eps = np.random.default_rng(0).standard_normal((3, T - 1, 4, 8))
+    a = CBFSSMHALF(config, seed=3)
+    a.inject_draws(eps[0]); a.evaluate_batch(u, y, ["train", "loss"], True)        # moves phi and fills the Adam slots
+    path = a.saver.save(Session(a), str(tmp_path / "model.ckpt"))
+    b = CBFSSMHALF(config, seed=99)                                                # a differently initialised net
+    assert not torch.equal(a.phi, b.phi)
+    b.saver.restore(Session(b), path)
+    assert torch.equal(a.phi, b.phi) and torch.equal(a.phi_m, b.phi_m) and torch.equal(a.phi_v, b.phi_v)
+    assert torch.equal(a.engine.theta, b.engine.theta) and a.engine.adam_t == b.engine.adam_t
+    outs = []
+    for m in (a, b):
+        m.inject_draws(eps[1])
+        pm, pv = m.evaluate_batch(u, y, ["pred_mean", "pred_var"], False)
+        m.inject_draws(eps[2])
+        m.evaluate_batch(u, y, ["train", "loss"], True)
+        outs.append((pm, pv, m.phi.clone(), m.engine.theta.clone()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
+    # a checkpoint of another recognition model is refused, not half-loaded
+    c = CBFSSMHALF(dict(config, recog_model="output"), seed=3)
+    with pytest.raises(ValueError):
+        c.saver.restore(Session(c), path)
