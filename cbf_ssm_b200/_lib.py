@@ -66,6 +66,7 @@ _SIGNATURES = {
     "cbf_timing_enable": (C.c_int, [C.c_int]),
     "cbf_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cbf_launches_read": (C.c_int, [C.POINTER(C.c_int64), C.c_int]),
+    "cbf_measure_fp32_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -980,6 +981,56 @@ CBF_API int cbf_launches_read(int64_t *count_host, int reset) {
   if (!count_host) { set_error("cbf_launches_read: NULL argument"); return CBF_ERR_NULL; }
   *count_host = (int64_t)g_launches;
   if (reset) g_launches = 0;
+  return 0;
+}
+
+// Measured FP32 roof of this GPU for bench.py's roofline: packed FMA (fma.rn.f32x2, the instruction the rollout
+// kernels' inner loops are made of), 8 independent accumulator pairs per thread, 8 CTAs of 256 threads per SM.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float s) {
+  auto pk = [](float x, float y) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; };
+  unsigned long long p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = pk(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f - i);
+  const unsigned long long ss = pk(s, s), h = pk(0.5f, 0.25f);
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(ss), "l"(h));
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p[i]));
+    t += x + y;
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
+CBF_API int cbf_measure_fp32_peak(float *scratch, int iters, double *tflops_host, void *stream) {
+  if (!scratch || !tflops_host) { set_error("cbf_measure_fp32_peak: NULL argument"); return CBF_ERR_NULL; }
+  if (iters < 1) { set_error("cbf_measure_fp32_peak: iters < 1"); return CBF_ERR_INVALID_SHAPE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  CBF_CUDA(cudaGetDevice(&dev));
+  CBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaEvent_t e0, e1;
+  CBF_CUDA(cudaEventCreate(&e0));
+  CBF_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {       // first repetition warms up; best of the rest
+    cudaEventRecord(e0, st);
+    fp32_peak_kernel<<<sms * 8, 256, 0, st>>>(scratch, iters, 0.999f); cbf_note_launch();
+    cudaEventRecord(e1, st);
+    CBF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CBF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 2.0 * 32.0 * (double)iters * 256.0 * 8.0 * sms;   // 2 lanes x 2 flop x 32 fma2 per iteration
+    if (rep > 0 && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops_host = best;
   return 0;
 }
 

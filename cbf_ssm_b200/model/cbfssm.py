@@ -152,23 +152,29 @@ class CBFSSM(BaseModel):
                             else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)))
         u, y = as_f32(u_host), as_f32(y_host)      # pinned tensors are copied asynchronously
         B, T, _ = u.shape
+        n0, nl = self._shard(B)
+        # decided from (N, world) alone, so every rank raises together instead of some entering the all-reduce
+        per = -(-(B * d.samples) // self.world)
+        if per * (self.world - 1) >= B * d.samples:
+            raise ValueError("minibatch has too few particles for this many ranks")
+        # this rank reads u, y only of the sequences its particles belong to: copy just those rows and make the
+        # particle offset relative to the first of them
+        b_lo, b_hi = n0 // d.samples, (n0 + nl - 1) // d.samples
+        u_part, y_part = u[b_lo:b_hi + 1], y[b_lo:b_hi + 1]
+        n0_rel = n0 - b_lo * d.samples
         # host -> device copies go on a side stream and overlap the generation of the step's normal draws
         main = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         self._copy_stream.wait_stream(main)
         with torch.cuda.stream(self._copy_stream):
-            ud = u.to(dev, non_blocking=True)
-            yd = y.to(dev, non_blocking=True)
-        n0, nl = self._shard(B)
-        # decided from (N, world) alone, so every rank raises together instead of some entering the all-reduce
-        per = -(-(B * d.samples) // self.world)
-        if per * (self.world - 1) >= B * d.samples:
-            raise ValueError("minibatch has too few particles for this many ranks")
+            ud = u_part.to(dev, non_blocking=True)
+            yd = y_part.to(dev, non_blocking=True)
         eb, zb, ef = self._draws(B, T, n0, nl)
         main.wait_stream(self._copy_stream)
         ud.record_stream(main)
         yd.record_stream(main)
+        n0 = n0_rel
         out = eng.forward(ud, yd, eb, zb, ef, condition=condition, n_offset=n0, n_local=nl)
         if "train" in names:
             eng.backward()                   # all-reduces gradient + terms when sharded

@@ -204,6 +204,11 @@ CBF_API int cbf_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t strea
 CBF_API int cbf_timing_enable(int enable);
 CBF_API int cbf_timing_read(double *ms_sum_host /*[8]*/, int64_t *count_host /*[8]*/);
 
+/* Measurement aid for bench.py's roofline denominator: runs a packed-FP32-FMA (fma.rn.f32x2) kernel that
+ * fills every SM and returns the measured TFLOP/s of this GPU (best of 3 after one warm-up; synchronises).
+ * scratch: at least 8 * 256 * (number of SMs) floats.  No reference counterpart. */
+CBF_API int cbf_measure_fp32_peak(float *scratch, int iters, double *tflops_host, void *stream);
+
 /* Number of kernels this library has launched on the calling host thread since the last reset
  * (measurement aid: bench.py's gpu_launches; there is no reference counterpart). */
 CBF_API int cbf_launches_read(int64_t *count_host, int reset);
