@@ -11,7 +11,7 @@ import torch
 
 from oracle import cbfssm_oracle as O      # only for PARAM_NAMES / shapes (checker side)
 from oracle import cbfssmhalf_oracle as H
-from tests.helpers import (HALF_REF_CASES, NAMED_CASES, STRONG_REF_CASES, elementwise_ok, half_ref_case, named_case,
+from tests.helpers import (HALF_REF_CASES, NAMED_CASES, STRONG_REF_CASES, elementwise_err, elementwise_ok, half_ref_case, named_case,
                            rel_inf, strong_ref_case)
 from tests.test_gpu_parity import run_engine
 
@@ -44,8 +44,10 @@ def _check(name, case, flags):
     bad = {k: v for k, v in worst.items() if not v < TOL}
     assert not bad, bad
     # the small tensors (kernel variance / lengthscales, noise terms): entry by entry
-    bad = [k for k in SMALL if not elementwise_ok(grads[k], gold["grad." + k], TOL)]
-    assert not bad, {k: (np.asarray(grads[k]).ravel(), gold["grad." + k].ravel()) for k in bad}
+    bad = {k: elementwise_err(grads[k], gold["grad." + k]) for k in SMALL}
+    print("elementwise", name, flags, {k: "%.1e" % v for k, v in bad.items()})
+    bad = {k: v for k, v in bad.items() if not v < TOL}
+    assert not bad, bad
     # one TF-Adam step on these gradients lands on the reference's updated variables (cbfssm.py:274-275).
     # Adam's first step is lr_t * g / (sqrt(.001) |g| + 1e-8): it forgets |g| unless |g| ~ 1e-8, so only entries
     # whose gradient is significant within its tensor are compared (the others amplify float32 noise by 1e8).

@@ -275,10 +275,16 @@ def test_bench_b200_arm_prints_the_contract_line():
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
         assert key in line, key
     assert line["n_gpus"] == 1 and line["scaling"] == "weak" and line["value"] > 0 and line["gpu_launches"] > 0
-    assert line["e2e"]["h2d_bytes_per_step"] == 64 * 300 * 4 * 4 and line["e2e"]["d2h_bytes_per_step"] == 8
+    # headline = the target shape (M=100, D=4, T=100): u [64,100,2] + y [64,100,2] float32 per step
+    assert line["e2e"]["h2d_bytes_per_step"] == 64 * 100 * 4 * 4 and line["e2e"]["d2h_bytes_per_step"] == 8
     assert 0 < line["e2e"]["value"] <= line["value"] * 1.05
+    assert line["config"]["M"] == 100 and line["config"]["dx"] == 4
     r = line["roofline"]
-    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"):
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "simt", "hbm"):
         assert key in r, key
-    assert 0 < r["frac"] < 1 and r["unit"] == "TFLOP/s"
+    # no fraction may exceed 1: tensor FLOPs against the tensor roof, O(M*D) FLOPs against the measured FP32 roof
+    assert r["bound"] == "tensor" and 0 < r["frac"] < 1 and 0 < r["simt"]["frac"] < 1 and r["unit"] == "TFLOP/s"
+    assert 60 < line["fp32_fma_peak_measured_tflops"] < 80
     assert "workload" in line["config"] and "model" not in line["config"]
+    x = line["extra"]["robomove_m20"]                  # BASELINE.json configs[1] in the same line
+    assert x["config"]["M"] == 20 and x["value"] > 0 and x["roofline"]["bound"] == "fp32_simt" and 0 < x["roofline"]["frac"] < 1
