@@ -31,7 +31,7 @@ class cbf_shape(C.Structure):
 
 
 class cbf_gp(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("Z", "ell", "sig2", "P", "alpha", "S")]
+    _fields_ = [(n, C.c_void_p) for n in ("Z", "ell", "sig2", "P", "alpha", "S", "state")]
 
 
 class cbf_grad_layout(C.Structure):
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cbf_elbo_backward_half": (C.c_int, [C.POINTER(cbf_shape), C.POINTER(cbf_gp)] + [_P] * 6
                                + [C.POINTER(C.c_double), _P, _P, _P, _P]),
     "cbf_export_states": (C.c_int, [C.POINTER(cbf_shape), _P, _P, _P, _P, _P]),
+    "cbf_state_sums": (C.c_int, [C.POINTER(cbf_shape), _P, _P, _P]),
     "cbf_moments": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "cbf_gp_prologue_state_doubles": (C.c_int64, [C.c_int32] * 3),
     "cbf_gp_prologue": (C.c_int, [C.c_int32] * 3 + [_P] * 14),
@@ -87,7 +88,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.cbf_abi_version() != 1:
+    if lib.cbf_abi_version() != 2:
         raise ImportError("libcbfssm_b200.so has an unexpected ABI version")
     _lib = lib
     return lib

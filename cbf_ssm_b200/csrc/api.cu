@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "dims_list.h"
+#include "f64_path.h"
 #include "kernels_outer.cuh"
 
 namespace cbf {
@@ -122,6 +123,8 @@ struct Plan {
   const DimOps *ops;
   bool half;                     // CBFSSMHALF: no backward-message GP, x_0 supplied by the caller
   size_t off_x0b;
+  bool f64;                      // float64 batched path (f64_path.cu): M > 128, dims without an instantiation, CBF_FLAG_FP64
+  size_t off_f64;
   // tensor-core path (16 <= M <= 128, enough particles)
   bool tc_fwd, tc_rev;
   size_t colsf, colsb;           // columns (live steps x particles) of the operand matrices
@@ -170,7 +173,15 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   const bool want_fast = !(s->flags & CBF_FLAG_FORCE_COOPERATIVE) &&
                          ((s->flags & CBF_FLAG_FORCE_REGISTER) || s->n_local >= kMinParticlesRegisterPath);
   p.ops = find_ops(s->dx, s->du, s->dy, s->M, want_fast);
-  if (need_ops && !p.ops) {
+  // float64 batched path: asked for, or the only one that can take the shape (M beyond the tensor path's 128, or
+  // dims without a compiled instantiation); it needs no per-dims kernels
+  p.f64 = (s->flags & CBF_FLAG_FP64) != 0 || s->M > 128 || !p.ops;
+  if (p.f64 && (s->dx + s->du + 1 > 32 || s->dx > 16)) {
+    set_error("float64 path: dims (dx=%d,du=%d,dy=%d) exceed dx <= 16, dx + du <= 31", s->dx, s->du, s->dy);
+    return CBF_ERR_UNSUPPORTED_DIMS;
+  }
+  if (p.f64) p.ops = nullptr;
+  if (need_ops && !p.ops && !p.f64) {
     set_error("dims (dx=%d,du=%d,dy=%d) are not compiled in (see csrc/dims_list.h)", s->dx, s->du, s->dy);
     return CBF_ERR_UNSUPPORTED_DIMS;
   }
@@ -299,7 +310,11 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
       p.off_carry_b = o; o = align_up(o + sizeof(float) * (p.chains.size() + 1) * p.dh * np, 256);
     }
   }
-  if (!coop_fits && !(p.tc_fwd && p.tc_rev)) {
+  if (p.f64) {
+    p.off_f64 = o;
+    o = align_up(o + f64_scratch_bytes(s->n_local, s->T, s->M, p.dx, p.dy, p.din), 256);
+  }
+  if (!p.f64 && !coop_fits && !(p.tc_fwd && p.tc_rev)) {
     set_error("M=%d: resident parameter set needs %zu B of shared memory (> %zu) and the tensor path (16 <= M <= 128) "
               "is not available for this call", s->M, coop_need, kMaxSmem);
     return CBF_ERR_UNSUPPORTED_M;
@@ -542,6 +557,35 @@ __global__ void export_states_kernel(Dims D, int dx, int dy, const float *__rest
   }
 }
 
+// Per-sequence partial sums [sum_s x, sum_s x^2] over THIS shard's particles (any particle range, not only
+// sequence-aligned ones): one warp per (local sequence row, t).  With the particles of a sequence spread over
+// ranks, tf.nn.moments over the particle axis (cbfssm.py:267-269) is an all-reduce of these sums.
+__global__ void state_sums_kernel(Dims D, int dx, Workspace ws, double *__restrict__ sums) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= D.B * D.T) return;
+  const int b = warp / D.T, t = warp - b * D.T;
+  const long long lo = (long long)b * D.S - D.n_offset, hi = lo + D.S;
+  const int n0 = (int)(lo < 0 ? 0 : lo), n1 = (int)(hi > D.n_local ? D.n_local : hi);
+  const size_t np = ws.npad;
+  for (int j = 0; j < dx; ++j) {
+    double s1 = 0.0, s2 = 0.0;
+    const float *xp = ws.X + ((size_t)t * dx + j) * np;
+    for (int n = n0 + lane; n < n1; n += 32) {
+      const double v = (double)xp[n];
+      s1 += v;
+      s2 += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      sums[((size_t)warp * dx + j) * 2] = s1;
+      sums[((size_t)warp * dx + j) * 2 + 1] = s2;
+    }
+  }
+}
+
 // tf.nn.moments(axes=[2]) over the particle axis (cbfssm.py:267-269): one warp per (b,t).
 __global__ void moments_kernel(const float *__restrict__ x, int rows, int S, int d, int d_keep,
                                const float *__restrict__ add_var, float *__restrict__ mean,
@@ -669,7 +713,9 @@ CBF_API const char *cbf_last_error_string(void) { return g_err; }
 
 CBF_API int cbf_supported(int32_t M, int32_t dx, int32_t du, int32_t dy) {
   const DimOps *ops = find_ops(dx, du, dy, M, true);
-  if (!ops || M < 1) return 0;
+  if (M < 1) return 0;
+  const bool f64_ok = dx >= 2 && dy >= 1 && dy < dx && du >= 0 && dx <= 16 && dx + du + 1 <= 32;
+  if (!ops || M > 128) return f64_ok ? 3 : 0;     // only the float64 batched path takes these
   bool coop_fits = true;
   for (int w = 0; w < 4; ++w)
     if (ops->smem_bytes(M, w) > kMaxSmem) coop_fits = false;
@@ -719,6 +765,13 @@ static int elbo_forward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace ws = bind_workspace(p, workspace);
   ws.x0 = x0;
+  if (p.f64) {
+    if (!gp_f->state || (!p.half && !gp_b->state)) { set_error("float64 path: cbf_gp.state (the cbf_gp_prologue state) is NULL"); return CBF_ERR_NULL; }
+    F64Args a{p.D, p.dx, p.du, p.dy, &p.chains, gp_f->state, p.half ? nullptr : gp_b->state, var_x, var_y, u, y, eps_b, z_b,
+              eps_f, ws, static_cast<char *>(workspace) + p.off_f64, st};
+    ScopedTiming tm(1, st);
+    return f64_forward(a, terms);
+  }
   const int nch = (int)p.chains.size();
   // tensor-core forward kernels: a 128-particle tile makes the M x M contraction a real GEMM
   const bool tc = p.tc_fwd;
@@ -785,6 +838,26 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
   const float w_ll = (float)term_weights_host[0], w_kl = (float)term_weights_host[1],
               w_en = (float)term_weights_host[2];
 
+  if (p.f64) {
+    if (!gp_f->state || (!p.half && !gp_b->state)) { set_error("float64 path: cbf_gp.state (the cbf_gp_prologue state) is NULL"); return CBF_ERR_NULL; }
+    F64Args a{p.D, p.dx, p.du, p.dy, &p.chains, gp_f->state, p.half ? nullptr : gp_b->state, var_x, var_y, u, y, eps_b, z_b,
+              eps_f, ws, static_cast<char *>(workspace) + p.off_f64, st};
+    F64Grad g{grad_flat, (long long)gl.total,
+              grad_flat + gl.f_P, grad_flat + gl.f_alpha, grad_flat + gl.f_S, grad_flat + gl.f_Z, grad_flat + gl.f_ell, grad_flat + gl.f_sig2,
+              grad_flat + gl.b_P, grad_flat + gl.b_alpha, grad_flat + gl.b_S, grad_flat + gl.b_Z, grad_flat + gl.b_ell, grad_flat + gl.b_sig2,
+              grad_flat + gl.var_x, grad_flat + gl.var_y};
+    {
+      ScopedTiming tm(2, st);
+      rc = f64_backward(a, term_weights_host[0], term_weights_host[1], term_weights_host[2], g);
+    }
+    if (rc) return rc;
+    if (p.half) {
+      const int nb = p.D.n_local / p.D.S;
+      reduce_x0b_kernel<<<ceil_div(nb * p.dx, 256), 256, 0, st>>>(ws.x0b, ws.npad, p.D.S, nb, p.dx, x0_bar); cbf_note_launch();
+      CBF_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   const int nch = (int)p.chains.size();
   if (p.tc_rev) {
     // ---- tensor-core path: rollout adjoints on tcgen05, parameter outer products as a tcgen05 split-K stream ----
@@ -927,6 +1000,18 @@ CBF_API int cbf_export_states(const cbf_shape *shape, const float *y, float *x_f
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   export_states_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p.D, p.dx, p.dy, y, ws, x_final, y_tilde); cbf_note_launch();
+  CBF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+CBF_API int cbf_state_sums(const cbf_shape *shape, double *sums, const void *workspace, void *stream) {
+  Plan p;
+  int rc = make_plan(shape, p, false);
+  if (rc) return rc;
+  if (!workspace || !sums) { set_error("cbf_state_sums: NULL argument"); return CBF_ERR_NULL; }
+  Workspace ws = bind_workspace(p, const_cast<void *>(workspace));
+  const int rows = p.D.B * p.D.T;
+  state_sums_kernel<<<ceil_div(rows * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p.D, p.dx, ws, sums); cbf_note_launch();
   CBF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -96,6 +96,13 @@ struct Dims {
   int ncond;   // conditioned state dims: dx (CBFSSM) or dy (CBFSSMHALF)
 };
 
+// The sparse-GP predictive variance sigma^2 - k.P k + sum_m a_m^2 S_md (gp_tf.py:140,159) is >= 0 in exact
+// arithmetic (k.(K_zz + jitter)^-1 k <= sigma^2), but the kernels form it in float32 from an explicit inverse, so
+// for ill-conditioned K_zz the cancellation error can push it below zero; the reference (float64 Cholesky
+// solves) never sees that.  Clamping at the exact lower bound keeps fvar + var_x >= var_x > 0, so the sqrt /
+// log / reciprocal that follow stay finite instead of turning the loss and Adam's update into NaN.
+__device__ __forceinline__ float gp_var_clamp(float v) { return fmaxf(v, 0.f); }
+
 inline __host__ __device__ int writer_run(int t, int R) { return (t % (2 * R)) < R ? 0 : 1; }
 
 // Layout of one reverse-pass accumulator block for a GP with (M, Din, Dout).
@@ -129,6 +136,30 @@ struct AccLayout {
     const int rg = m / TR, i = m - rg * TR, cg = col / TC, j = col - cg * TC;
     const int tile = rg * CG + cg;
     return interleaved ? ((size_t)tile * TR + i) * TC + j : ((size_t)i * ntiles + tile) * TC + j;
+  }
+};
+
+// float64 state of one GP's prologue (cbf_gp_prologue): constrained parameters, K_zz, P = (K_zz + 1e-8 I)^-1,
+// alpha = P m, sigmoids for the adjoint, scratch.
+struct ProState {   // offsets (doubles) into the caller's state buffer
+  int64_t ell, sgl, sig2, sgv, S, sgS, m, Zt, K0, P, alpha, W1, W2, total;
+  __host__ __device__ ProState(int M, int Din, int Dout) {
+    int64_t o = 0;
+    ell = o; o += Din;
+    sgl = o; o += Din;
+    sig2 = o; o += 1;
+    sgv = o; o += 1;
+    S = o; o += (int64_t)M * Dout;
+    sgS = o; o += (int64_t)M * Dout;
+    m = o; o += (int64_t)M * Dout;
+    Zt = o; o += (int64_t)M * Din;
+    K0 = o; o += (int64_t)M * M;
+    P = o; o += (int64_t)M * M;
+    alpha = o; o += (int64_t)M * Dout;
+    const int64_t w = (int64_t)M * (M > Din ? M : Din);   // scratch, also holds an [M, Din] temporary
+    W1 = o; o += w;
+    W2 = o; o += w;
+    total = o;
   }
 };
 

@@ -373,7 +373,7 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
     for (int d = 0; d < DOUT; ++d) fv[d] = fmaf(a2, S[d], fv[d]);
   }
 #pragma unroll
-  for (int d = 0; d < DOUT; ++d) fv[d] = g.sig2 - q + fv[d];
+  for (int d = 0; d < DOUT; ++d) fv[d] = gp_var_clamp(g.sig2 - q + fv[d]);
 }
 
 // ---- per-warp staging tile + accumulation of the parameter adjoints ----

@@ -150,7 +150,7 @@ __device__ __forceinline__ void gp_forward_coop(const GpS<DIN, DOUT> &g, float *
     }
   }
 #pragma unroll
-  for (int d = 0; d < DOUT; ++d) fv[d] = g.sig2 - q + fv[d];
+  for (int d = 0; d < DOUT; ++d) fv[d] = gp_var_clamp(g.sig2 - q + fv[d]);
 }
 
 // ---- reverse of one GP evaluation (SURVEY 8a note 4) ----

@@ -506,7 +506,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) {
     fm[d] *= c.sig2 * kscale;
-    fv[d] = c.sig2 - ps * s4 * k2 * q + ps * ps * s4 * k2 * fv[d];
+    fv[d] = gp_var_clamp(c.sig2 - ps * s4 * k2 * q + ps * ps * s4 * k2 * fv[d]);
   }
   tc_fence_before();   // order this step's tcgen05.ld before the next barrier / MMA
 }

@@ -10,28 +10,6 @@
 
 namespace cbf {
 
-struct ProState {   // offsets (doubles) into the caller's state buffer
-  int64_t ell, sgl, sig2, sgv, S, sgS, m, Zt, K0, P, alpha, W1, W2, total;
-  __host__ __device__ ProState(int M, int Din, int Dout) {
-    int64_t o = 0;
-    ell = o; o += Din;
-    sgl = o; o += Din;
-    sig2 = o; o += 1;
-    sgv = o; o += 1;
-    S = o; o += (int64_t)M * Dout;
-    sgS = o; o += (int64_t)M * Dout;
-    m = o; o += (int64_t)M * Dout;
-    Zt = o; o += (int64_t)M * Din;
-    K0 = o; o += (int64_t)M * M;
-    P = o; o += (int64_t)M * M;
-    alpha = o; o += (int64_t)M * Dout;
-    const int64_t w = (int64_t)M * (M > Din ? M : Din);   // scratch, also holds an [M, Din] temporary
-    W1 = o; o += w;
-    W2 = o; o += w;
-    total = o;
-  }
-};
-
 __device__ __forceinline__ double softplus_d(double x) {
   return (x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x))) + 1e-10;
 }

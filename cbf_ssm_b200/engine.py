@@ -120,7 +120,8 @@ class _GpBuffers:
         self.P, self.alpha, self.S = z(M, M), z(M, dout), z(M, dout)
         self.kl = torch.zeros(1, dtype=F64, device=device)
         self.state = torch.zeros(int(lib.cbf_gp_prologue_state_doubles(M, din, dout)), dtype=F64, device=device)
-        self.c = cbf_gp(*(C.c_void_p(t.data_ptr()) for t in (self.Z, self.ell, self.sig2, self.P, self.alpha, self.S)))
+        self.c = cbf_gp(*(C.c_void_p(t.data_ptr()) for t in (self.Z, self.ell, self.sig2, self.P, self.alpha, self.S,
+                                                              self.state)))
 
 
 class ElboEngine:
@@ -135,7 +136,7 @@ class ElboEngine:
         self.kernel_path = self.lib.cbf_supported(d.ind_pnt_num, d.dim_x, d.dim_u, d.dim_y)
         if not self.kernel_path:
             raise _lib.CbfError(-2, f"M={d.ind_pnt_num}, dims=({d.dim_x},{d.dim_u},{d.dim_y}) not supported by the "
-                                    "compiled library (csrc/dims_list.h; M limited by shared memory)")
+                                    "compiled library (float64 path: dim_x <= 16, dim_x + dim_u <= 31)")
         # ---- flat float64 parameter vector with named views ----
         shapes = param_shapes(d)
         self.names = tuple(shapes)
@@ -361,6 +362,14 @@ class ElboEngine:
         yt = None if d.half else torch.empty_like(xf)       # CBFSSMHALF has no y_tilde
         check(self.lib.cbf_export_states(C.byref(shape), ptr(y), ptr(xf), ptr(yt), ptr(self._ws), self._stream()))
         return xf, yt
+
+    def state_sums(self):
+        """[B, T, dx, 2] float64 (sum_s x, sum_s x^2) of the last forward over this shard's particles
+        (sharded prediction moments: all-reduce, then mean = s1/S, var = s2/S - mean^2)."""
+        shape, d = self._shape, self.dims
+        sums = torch.empty(shape.B, shape.T, d.dim_x, 2, dtype=F64, device=self.device)
+        check(self.lib.cbf_state_sums(C.byref(shape), ptr(sums), ptr(self._ws), self._stream()))
+        return sums
 
     def moments(self, x, d_keep, add_var=None):
         """tf.nn.moments(axes=[2]) (+ add_var) over the particle axis of [nb,T,S,d]."""

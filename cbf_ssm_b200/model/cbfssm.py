@@ -187,16 +187,31 @@ class CBFSSM(BaseModel):
         res = {}
         if any(n in _PRED for n in names):
             if self.world > 1:
-                raise NotImplementedError("prediction handles run on one GPU (replicas only, SURVEY 8e)")
-            xf, yt = eng.export_states(yd)
-            pm, pv = eng.moments(xf, d.dim_y, eng.var_y)
-            im, iv = eng.moments(xf, d.dim_x, None)
-            res.update(x_final=xf, y_tilde=yt, y_final=xf[..., :d.dim_y], pred_mean=pm, pred_var=pv,
-                       internal_mean=im, internal_var=iv)
+                # the particles of a sequence are spread over ranks: moments over the particle axis become one
+                # all-reduce of per-sequence [sum x, sum x^2] (cbfssm.py:267-269)
+                if any(n in ("x_final", "y_final", "y_tilde") for n in names):
+                    raise NotImplementedError("per-particle states are not gathered across ranks; fetch the moments")
+                sums = torch.zeros(B, T, d.dim_x, 2, dtype=torch.float64, device=dev)
+                sums[b_lo:b_hi + 1] = eng.state_sums()
+                torch.distributed.all_reduce(sums, group=self._group)
+                mean = sums[..., 0] / d.samples
+                var = sums[..., 1] / d.samples - mean * mean
+                yfull = y.to(dev)
+                pm = mean[..., :d.dim_y].float()
+                pv = (var[..., :d.dim_y] + eng.var_y[:d.dim_y].double()).float()
+                res.update(pred_mean=pm, pred_var=pv, internal_mean=mean.float(), internal_var=var.float())
+                yd_all = yfull
+            else:
+                xf, yt = eng.export_states(yd)
+                pm, pv = eng.moments(xf, d.dim_y, eng.var_y)
+                im, iv = eng.moments(xf, d.dim_x, None)
+                res.update(x_final=xf, y_tilde=yt, y_final=xf[..., :d.dim_y], pred_mean=pm, pred_var=pv,
+                           internal_mean=im, internal_var=iv)
+                yd_all = yd
             if "mse" in names:   # tf.losses.mean_squared_error casts to float32 (cbfssm.py:270)
-                res["mse"] = torch.mean((pm - yd) ** 2)
+                res["mse"] = torch.mean((pm - yd_all) ** 2)
             if "sde" in names:
-                res["sde"] = torch.abs(pm - yd) / torch.sqrt(pv)
+                res["sde"] = torch.abs(pm - yd_all) / torch.sqrt(pv)
         res.update(loss=out["loss"], entropy=out["entropy"], kl_x=out["kl_x"])
         vals = []
         for n in names:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CBF_ABI_VERSION 1
+#define CBF_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CBF_API __attribute__((visibility("default")))
@@ -71,6 +71,13 @@ typedef struct cbf_shape {
 /* CBFSSMHALF (cbfssm/model/cbfssmhalf.py): no backward-message GP, x_0 supplied by the caller's
  * recognition model, only the first dy state dims are conditioned.  Use the *_half entry points. */
 #define CBF_FLAG_HALF_MODEL 32
+/* Float64 batched path (any M, any dims with dx <= 16, dx + du <= 31): per time step all particles are one
+ * batch -- kernel matrix, one DGEMM against P, moments, step arithmetic -- as the reference graph itself is
+ * laid out (cbfssm.py:107-111,176-179), entirely in float64 between stored states.  Selected automatically for
+ * M > 128 (P no longer fits an SM) and for dims without a compiled instantiation; set the flag for inducing
+ * sets whose cond(K_zz) is beyond float32's reach (crowded inducing points), where the float32 paths are
+ * accuracy-limited.  Needs cbf_gp.state. */
+#define CBF_FLAG_FP64 128
 
 
 /* Kernel-level operands of one sparse GP (gp_tf.py:103-130), float32, produced by
@@ -82,6 +89,8 @@ typedef struct cbf_gp {
   const float *P;      /* [M, M]      (K_zz + 1e-8 I)^-1, symmetric             */
   const float *alpha;  /* [M, Dout]   P @ zeta_mean                             */
   const float *S;      /* [M, Dout]   zeta_var (constrained)                    */
+  const double *state; /* the float64 state buffer cbf_gp_prologue filled (holds P, alpha, S, Z/ell,
+                          ell, sig2 in float64); read by the float64 path only, may be NULL otherwise */
 } cbf_gp;
 
 /* Offsets (in doubles) into the flat kernel-level gradient vector written by
@@ -96,8 +105,9 @@ typedef struct cbf_grad_layout {
 CBF_API int         cbf_abi_version(void);
 CBF_API const char *cbf_last_error_string(void);
 
-/* 0: not supported; 1: cooperative kernels only; 2: register-resident kernels compiled in
- * for exactly this (M, dims) (used by default). */
+/* 0: not supported; 1: cooperative / tensor-core kernels; 2: register-resident kernels compiled in
+ * for exactly this (M, dims) (used by default); 3: only the float64 batched path takes the shape
+ * (M > 128, or dims without a compiled instantiation). */
 CBF_API int cbf_supported(int32_t M, int32_t dx, int32_t du, int32_t dy);
 
 /* Bytes of caller-allocated device workspace one forward+backward needs. */
@@ -153,6 +163,12 @@ CBF_API int cbf_elbo_backward_half(const cbf_shape *shape, const cbf_gp *gp_f,
  * nb*S == n_local required. Either pointer may be NULL. */
 CBF_API int cbf_export_states(const cbf_shape *shape, const float *y,
                       float *x_final, float *y_tilde, const void *workspace, void *stream);
+
+/* Per-sequence partial sums of the forward states over THIS shard's particles, for tf.nn.moments over the
+ * particle axis (cbfssm.py:267,269) when the particles of a sequence are split over ranks (any particle range):
+ * sums [B, T, dx, 2] float64 = (sum_s x, sum_s x^2); sequences without a local particle get zeros.  The caller
+ * all-reduces `sums` and forms mean = s1/S, var = s2/S - mean^2 (+ var_y for pred_var, cbfssm.py:268). */
+CBF_API int cbf_state_sums(const cbf_shape *shape, double *sums, const void *workspace, void *stream);
 
 /* tf.nn.moments(axes=[2]) of cbfssm.py:267-269 over the particle axis of a
  * [nb, T, S, d] tensor: mean and population variance (+ add_var[j] if non-NULL). */

@@ -25,7 +25,7 @@ def _problem(dx, du, dy, M, S, B, T, R, kap, seed=5):
     return cfg, H.init_params_half(cfg, seed), u, y, eps_f
 
 
-@pytest.mark.parametrize("flags", [12, 1, 12 | 64], ids=["register_or_tensor", "cooperative", "tensor_time_windows"])
+@pytest.mark.parametrize("flags", [12, 1, 12 | 64, 128], ids=["register_or_tensor", "cooperative", "tensor_time_windows", "float64"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "dx%d_du%d_dy%d_M%d_S%d_B%d_T%d_R%d" % c[:8])
 def test_half_elbo_and_gradients_match_oracle(case, flags, monkeypatch):
     from cbf_ssm_b200.engine import ElboEngine, ModelDims

@@ -141,9 +141,11 @@ def test_unsupported_shapes_fail_loudly():
     from cbf_ssm_b200._lib import CbfError
     from cbf_ssm_b200.engine import ElboEngine, ModelDims
     with pytest.raises(CbfError):
-        ElboEngine(ModelDims(5, 5, 2, 20, 5, 4))        # dims not compiled in
+        ElboEngine(ModelDims(17, 2, 5, 20, 5, 4))       # beyond every path (float64 path: dim_x <= 16)
     with pytest.raises(CbfError):
-        ElboEngine(ModelDims(4, 2, 2, 500, 5, 4))       # M = 500 does not fit one SM (round-1 limit)
+        ElboEngine(ModelDims(4, 40, 2, 20, 5, 4))       # dim_x + dim_u > 31
+    assert ElboEngine(ModelDims(4, 2, 2, 500, 5, 4)).kernel_path == 3      # M = 500: float64 batched path
+    assert ElboEngine(ModelDims(5, 5, 2, 20, 5, 4)).kernel_path == 3       # dims without an instantiation
 
 
 def test_adam_step_matches_tf_formula():

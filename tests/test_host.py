@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.cbf_abi_version() == 1
+    assert lib.cbf_abi_version() == 2
 
 
 def _shape(**kw):
@@ -40,10 +40,13 @@ def test_host_only_entry_points_without_gpu(lib):
     assert lib.cbf_supported(20, 4, 2, 2) == 2          # register-resident instantiation
     assert lib.cbf_supported(100, 4, 1, 1) == 1
     assert lib.cbf_supported(100, 14, 7, 7) == 1
-    assert lib.cbf_supported(20, 5, 5, 5) == 0          # dims not compiled in
-    assert lib.cbf_supported(500, 4, 2, 2) == 0         # resident set exceeds one SM
+    assert lib.cbf_supported(20, 5, 5, 5) == 0          # dy >= dx is not a model
+    assert lib.cbf_supported(20, 5, 5, 2) == 3          # dims not compiled in: the float64 batched path takes them
+    assert lib.cbf_supported(500, 4, 2, 2) == 3         # resident set exceeds one SM: float64 batched path
+    assert lib.cbf_supported(500, 8, 1, 4) == 3 and lib.cbf_supported(129, 4, 2, 2) == 3
     assert lib.cbf_supported(128, 4, 2, 2) == 1         # too large for the cooperative kernels: tensor path only
-    assert lib.cbf_supported(128, 14, 7, 7) == 1 and lib.cbf_supported(129, 4, 2, 2) == 0
+    assert lib.cbf_supported(128, 14, 7, 7) == 1
+    assert lib.cbf_supported(20, 17, 2, 5) == 0 and lib.cbf_supported(20, 16, 16, 5) == 0   # beyond the float64 path's dims
     n = C.c_size_t(0)
     s = _shape()
     assert lib.cbf_workspace_bytes(C.byref(s), C.byref(n)) == 0 and n.value > 0
