@@ -55,6 +55,9 @@ WORKLOADS = {
     # BASELINE.json configs[4]: the 2^20-particle corner at M=100, D=4 (strong-scaling subject: --scaling strong)
     "sweep_1m_m100": dict(dx=4, du=2, dy=2, M=100, S=1024, T=500, R=16, kap=1.0, lf=(10.0, 0.0), batch=1024, cpu_batch=1,
                           name="sweep corner CBF-SSM dx4/du2/dy2 M100 S1024 B1024 (2^20 particles) T500 R16 (BASELINE.json configs[4])"),
+    # BASELINE.json configs[4] corner M=500, D=8: the float64 batched path (P = 2 MB no longer fits an SM)
+    "sweep_d8_m500": dict(dx=8, du=1, dy=4, M=500, S=1024, T=500, R=16, kap=1.0, lf=(10.0, 0.0), batch=16, cpu_batch=1,
+                          name="sweep corner CBF-SSM dx8/du1/dy4 M500 S1024 T500 R16 (BASELINE.json configs[4]), float64 batched path"),
     # BASELINE.json configs[3]: Voliro-shaped multi-experiment windows, 256 sequences x 1024 particles per GPU
     "voliro_m20": dict(dx=13, du=6, dy=7, M=20, S=1024, T=64, R=16, kap=1.0, lf=(20.0, 0.0), batch=256, cpu_batch=2,
                        name="Voliro-shaped CBF-SSM dx13/du6/dy7 M20 S1024 T64 R16 (BASELINE.json configs[3])"),
@@ -353,7 +356,19 @@ def measure_workload(name, args, steps, ctx):
                e2e_ms=e2e_ms, e2e_value=psteps_global / (e2e_ms * 1e-3), loss=float(loss), launches=launches,
                clocks=clocks, kms=[kms[i] / steps for i in range(8)], kcnt=[int(kcnt[i]) for i in range(8)],
                h2d=u_host.numel() * 4 + y_host.numel() * 4, steps=steps, warm=warm,
-               tensor_path=bool(kcnt[4] or kcnt[5]), ws_bytes=int(eng._ws.numel()) if eng._ws is not None else 0)
+               tensor_path=bool(kcnt[4] or kcnt[5]), ws_bytes=int(eng._ws.numel()) if eng._ws is not None else 0,
+               f64_path=bool(eng.kernel_path == 3 or (int(args.flags) & 128)))
+    if out["f64_path"]:      # measured FP64 GEMM roof of this GPU (cuBLAS DGEMM through torch, best of 5)
+        a64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        best = 0.0
+        for _ in range(6):
+            ev0.record()
+            torch.matmul(a64, a64)
+            ev1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2 * 4096 ** 3 / (ev0.elapsed_time(ev1) * 1e-3) / 1e12)
+        out["dgemm_peak"] = best
+        del a64
     del model, eng
     torch.cuda.empty_cache()
     return out
@@ -398,6 +413,20 @@ def roofline_of(m, peaks, peaks_src, fp32_peak, traffic_table, workload_key):
                       "algorithmic_bytes_per_launch": bytes_pstep * nl * T // 4,
                       "dram_bytes_over_algorithmic": (traffic / (bytes_pstep * nl * T / 4.0)) if traffic else None,
                       "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src}}
+    if m.get("f64_path"):
+        # float64 batched path: kinds 1 / 2 time the whole forward / backward pass; the M^2 work is cuBLAS DGEMM
+        t_f, t_b = m["kms"][1] * 1e-3, m["kms"][2] * 1e-3
+        f_fwd = ev_f * ff["fwd_m2"] + ev_b * fb["fwd_m2"]
+        f_bwd = ev_f * (ff["fwd_m2"] + ff["bwd_m2"]) + ev_b * (fb["fwd_m2"] + fb["bwd_m2"])   # the reverse pass recomputes a = P k
+        a_t = f_bwd / t_b / 1e12
+        return {"bound": "tensor", "kernel": "f64 backward pass (DGEMM + elementwise kernels)", "achieved": a_t,
+                "peak": m["dgemm_peak"], "unit": "TFLOP/s", "frac": a_t / m["dgemm_peak"], "traffic": None,
+                "peak_source": "FP64 GEMM rate measured on this GPU in this run (cuBLAS DGEMM 4096^3 through torch, best of 6)",
+                "forward_pass": {"achieved": f_fwd / t_f / 1e12, "ms": m["kms"][1]}, "backward_pass_ms": m["kms"][2],
+                "note": "M^2 FLOPs incl. the recomputation of a = P k in the reverse pass (it is a DGEMM here); the [n, M] "
+                        "matrices make the elementwise kernels HBM-bound",
+                "live_message_evaluations_of_2T": [live, 2 * T],
+                "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src}}
     if m["tensor_path"]:
         a_t = ev * m2 / t_s / 1e12
         a_s = ev * md / t_s / 1e12
@@ -470,7 +499,8 @@ def run_b200(args):
     d = describe(main, args.workload)
     line = {"metric": METRIC, "value": d["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": main["warm"], "ms_per_step": d["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": d["config"], "clocks": d["clocks"],
+            "vs_baseline": None, "dtype": "f64" if main.get("f64_path") else "f32", "data": "synthetic",
+            "config": d["config"], "clocks": d["clocks"],
             "e2e": d["e2e"], "gpu_launches": d["gpu_launches"], "roofline": d["roofline"],
             "l2_working_set_mib": d["l2_working_set_mib"],
             "fp32_fma_peak_measured_tflops": fp32_peak}
