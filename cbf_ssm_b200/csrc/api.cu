@@ -123,6 +123,8 @@ struct Plan {
   const DimOps *ops;
   bool half;                     // CBFSSMHALF: no backward-message GP, x_0 supplied by the caller
   size_t off_x0b;
+  size_t off_kaf, off_kab;       // register path: saved evaluations (0 = not saved)
+  bool save_eval;
   bool f64;                      // float64 batched path (f64_path.cu): M > 128, dims without an instantiation, CBF_FLAG_FP64
   size_t off_f64;
   // tensor-core path (16 <= M <= 128, enough particles)
@@ -147,6 +149,18 @@ static size_t tc_window_budget() {
     if (v > 0) return (size_t)v;
   }
   return kTcWindowBytes;
+}
+// Budget for the register path's saved evaluations (176-192 B per GP evaluation at M = 20: 37 GB at the bench
+// shape of 227 200 particles x 300 steps); larger problems recompute in the reverse pass as before.
+// CBFSSM_B200_SAVE_EVAL_BYTES overrides it (0 disables saving).
+constexpr size_t kSavedEvalBytes = (size_t)64 << 30;
+static size_t saved_eval_budget() {
+  const char *e = getenv("CBFSSM_B200_SAVE_EVAL_BYTES");
+  if (e != nullptr && *e) {
+    const long long v = atoll(e);
+    if (v >= 0) return (size_t)v;
+  }
+  return kSavedEvalBytes;
 }
 constexpr int kOuterMaxGrid = 148 * 2;
 
@@ -203,6 +217,18 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   p.ptiles = ceil_div(s->n_local, kNP);            // upper bound for every path (smallest CTA tile)
   p.chains = build_chains(s->T, s->R);
   if (p.half) p.chains.clear();
+  if ((s->flags & CBF_FLAG_PREDICT_ONLY) && !s->condition) {
+    // Free-running prediction (cbfssm.py:227-228): the rollout is conditioned only while t < R - 1, so of the
+    // backward message only y2[0 .. R-1] is ever read -- keep the chains that write one of those steps (one
+    // chain of <= 2R steps instead of ~2T)
+    std::vector<Chain> need;
+    for (const Chain &c : p.chains) {
+      bool used = false;
+      for (int t = c.t_lo; t <= c.t_hi && t <= s->R - 1; ++t) used = used || writer_run(t, s->R) == c.run;
+      if (used) need.push_back(c);
+    }
+    p.chains.swap(need);
+  }
   p.slots_per_cta = 1;
   if (p.ops) {
     p.ops->layouts(s->M, &p.Lf, &p.Lb);
@@ -226,6 +252,17 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   p.off_stats = o; o = align_up(o + sizeof(double) * (p.dy + 2), 256);
   p.off_cpack = o; o = align_up(o + sizeof(float) * 2 * 2048, 256);
   p.off_x0b = o; o = align_up(o + sizeof(float) * p.dx * np, 256);
+  // ---- register path: keep every GP evaluation (k, a, fmean, fvar) for the reverse pass when it fits ----
+  p.save_eval = false; p.off_kaf = p.off_kab = 0;
+  if (p.ops && p.ops->fixed_M && p.ops->saved_planes && !(s->flags & CBF_FLAG_PREDICT_ONLY) && s->T > 1) {
+    const size_t bf = sizeof(float4) * (size_t)p.ops->saved_planes(0) * np * (size_t)(s->T - 1);
+    const size_t bb = p.half ? 0 : sizeof(float4) * (size_t)p.ops->saved_planes(1) * np * (size_t)(2 * s->T);
+    if (bf + bb <= saved_eval_budget()) {
+      p.save_eval = true;
+      p.off_kaf = o; o = align_up(o + bf, 256);
+      p.off_kab = o; o = align_up(o + bb + 16, 256);
+    }
+  }
   // ---- tensor-core path ----
   p.tc_fwd = p.tc_rev = false;
   if (p.ops && p.ops->fw_forward_tc != nullptr && s->M >= kMinTensorM && s->M <= 128 &&
@@ -376,6 +413,8 @@ static Workspace bind_workspace(const Plan &p, void *base) {
   w.cpack = reinterpret_cast<float *>(b + p.off_cpack);
   w.carry_f = p.tc_rev ? reinterpret_cast<float *>(b + p.off_carry_f) : nullptr;
   w.carry_b = p.tc_rev ? reinterpret_cast<float *>(b + p.off_carry_b) : nullptr;
+  w.KAf = p.save_eval ? reinterpret_cast<float4 *>(b + p.off_kaf) : nullptr;
+  w.KAb = (p.save_eval && !p.half) ? reinterpret_cast<float4 *>(b + p.off_kab) : nullptr;
   w.x0 = nullptr;
   w.x0b = reinterpret_cast<float *>(b + p.off_x0b);
   w.npad = p.D.npad;
@@ -822,6 +861,10 @@ static int elbo_backward_impl(const cbf_shape *shape, const cbf_gp *gp_f, const 
   int rc = make_plan(shape, p, true);
   if (rc) return rc;
   if ((rc = check_gp(gp_f, "gp_f")) || (!p.half && (rc = check_gp(gp_b, "gp_b")))) return rc;
+  if (shape->flags & CBF_FLAG_PREDICT_ONLY) {
+    set_error("cbf_elbo_backward: the forward pass ran with CBF_FLAG_PREDICT_ONLY (no entropy, partial message)");
+    return CBF_ERR_INVALID_SHAPE;
+  }
   if (!var_x || !var_y || !u || !y || (!p.half && (!eps_b || !z_b)) || (p.half && (!x0 || !x0_bar)) ||
       (!eps_f && shape->T > 1) || !term_weights_host || !grad_flat || !workspace) {
     set_error("cbf_elbo_backward: NULL argument");

@@ -83,6 +83,8 @@ struct Workspace {
   float *carry_f;  // [dx][npad]            state adjoint between time windows (tensor path)
   float *carry_b;  // [chains][dh][npad]    message adjoint between chain pieces (tensor path)
   float *cpack;    // [2][2048] packed constant-bank images of the two GPs (register path)
+  float4 *KAf;     // register path, optional: saved (k, a, fmean, fvar) of every forward-rollout GP evaluation
+  float4 *KAb;     //                          ... of every backward-message evaluation, slot = run * T + t
   const float *x0; // CBFSSMHALF: x_0 per sequence [B][dx] (output of the recognition model)
   float *x0b;      // CBFSSMHALF: adjoint of x_0 per particle [dx][npad]
   int npad;
@@ -193,6 +195,7 @@ struct DimOps {
   size_t (*smem_bytes)(int M, int which);  // which: 0 bm_fwd 1 fw_fwd 2 fw_rev 3 bm_rev
   int (*occupancy)(int M, int which);      // resident CTAs/SM of the persistent reverse kernels
   void (*layouts)(int M, AccLayout *Lf, AccLayout *Lb);   // accumulator layouts of the two reverse kernels
+  int (*saved_planes)(int which);          // register path: float4 planes of one saved evaluation (0 forward GP, 1 message GP); else nullptr
   int slots_per_cta;                       // partial-sum slots each reverse CTA writes
   int particles_per_cta;                   // particle tile of one CTA
   int fixed_M;                             // 0: any M (cooperative path); else the compiled-in M

@@ -329,8 +329,8 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
       float m0, m1, v0, v1;
       unpack2(fm2[d], m0, m1);
       unpack2(fv2[d], v0, v1);
-      fm[2 * d] = m0; fv[2 * d] = g.sig2 - q + v0;
-      if (2 * d + 1 < DOUT) { fm[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = m1; fv[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = g.sig2 - q + v1; }
+      fm[2 * d] = m0; fv[2 * d] = gp_var_clamp(g.sig2 - q + v0);
+      if (2 * d + 1 < DOUT) { fm[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = m1; fv[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = gp_var_clamp(g.sig2 - q + v1); }
     }
     return;
   }
@@ -374,6 +374,79 @@ __device__ __forceinline__ void gp_forward_fast(const GpF<M, DIN, DOUT, SLOT> &g
   }
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) fv[d] = gp_var_clamp(g.sig2 - q + fv[d]);
+}
+
+// Saved GP evaluation of one particle-step: the forward kernels can leave (k, a = P k, fmean, fvar) in HBM as
+// NPL float4 planes of npad particles (plane pl of evaluation slot e at (e * NPL + pl) * npad + n: a warp moves
+// 512 contiguous bytes per plane), and the reverse kernels then load them instead of recomputing the
+// evaluation -- about a quarter of their FMA-pipe cycles (the kernel vector and the M x M contraction) for
+// 16 * NPL bytes per evaluation each way; the kernels sit at a few % of the HBM roof, so the trade is free
+// until the extra workspace no longer fits (api.cu decides).
+template <int MP, int DOUT>
+struct SavedEval {
+  static constexpr int NK = MP / 4, NF = (2 * DOUT + 3) / 4, NPL = 2 * NK + NF;
+  static_assert(MP % 4 == 0, "MP is a multiple of 4");
+  static __device__ __forceinline__ void store(float4 *__restrict__ base, size_t slot, size_t np, int nl,
+                                               const float (&k)[MP], const float (&a)[MP], const float (&fm)[DOUT],
+                                               const float (&fv)[DOUT]) {
+    float4 *p = base + slot * NPL * np + nl;
+#pragma unroll
+    for (int i = 0; i < NK; ++i) p[(size_t)i * np] = make_float4(k[4 * i], k[4 * i + 1], k[4 * i + 2], k[4 * i + 3]);
+#pragma unroll
+    for (int i = 0; i < NK; ++i) p[(size_t)(NK + i) * np] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    float f[4 * NF];
+#pragma unroll
+    for (int d = 0; d < 4 * NF; ++d) f[d] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) { f[d] = fm[d]; f[DOUT + d] = fv[d]; }
+#pragma unroll
+    for (int i = 0; i < NF; ++i) p[(size_t)(2 * NK + i) * np] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  }
+  static __device__ __forceinline__ void load_ka(const float4 *__restrict__ base, size_t slot, size_t np, int nl,
+                                                 float (&k)[MP], float (&a)[MP]) {
+    const float4 *p = base + slot * NPL * np + nl;
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {
+      const float4 v = p[(size_t)i * np];
+      k[4 * i] = v.x; k[4 * i + 1] = v.y; k[4 * i + 2] = v.z; k[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {
+      const float4 v = p[(size_t)(NK + i) * np];
+      a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+    }
+  }
+  static __device__ __forceinline__ void load_f(const float4 *__restrict__ base, size_t slot, size_t np, int nl,
+                                                float4 (&q)[NF]) {
+    const float4 *p = base + slot * NPL * np + nl;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) q[i] = p[(size_t)(2 * NK + i) * np];
+  }
+  static __device__ __forceinline__ void unpack_f(const float4 (&q)[NF], float (&fm)[DOUT], float (&fv)[DOUT]) {
+    float f[4 * NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) { f[4 * i] = q[i].x; f[4 * i + 1] = q[i].y; f[4 * i + 2] = q[i].z; f[4 * i + 3] = q[i].w; }
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) { fm[d] = f[d]; fv[d] = f[DOUT + d]; }
+  }
+};
+
+// x~ = x / ell as gp_forward_fast forms it (for the reverse kernels when the evaluation itself is loaded)
+template <int M, int DIN, int DOUT, int SLOT>
+__device__ __forceinline__ void gp_scale_input(const GpF<M, DIN, DOUT, SLOT> &g, const float (&xin)[DIN],
+                                               float (&xt)[GpF<M, DIN, DOUT, SLOT>::DINP]) {
+  using G = GpF<M, DIN, DOUT, SLOT>;
+  constexpr int DINP = G::DINP;
+  if constexpr (kConstOps) {
+    using C = typename G::C;
+#pragma unroll
+    for (int j = 0; j < DINP; ++j) xt[j] = (j < DIN) ? xin[j < DIN ? j : 0] * C::il(j < DIN ? j : 0) : 0.f;
+  } else {
+    float il[DINP];
+    ld_row<DINP>(g.il, il);
+#pragma unroll
+    for (int j = 0; j < DINP; ++j) xt[j] = (j < DIN) ? xin[j < DIN ? j : 0] * il[j] : 0.f;
+  }
 }
 
 // ---- per-warp staging tile + accumulation of the parameter adjoints ----
@@ -726,7 +799,7 @@ __device__ __forceinline__ void cta_sum_store(const float (&vals)[COUNT], float 
 }
 
 // =====================================================================================
-template <int DX, int DU, int DY, int M>
+template <int DX, int DU, int DY, int M, bool SAVE>
 __global__ void __launch_bounds__(kFastThreads) bm_forward_fast_kernel(
     Dims D, ChainTable chains, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ u,
     const float *__restrict__ y, const float *__restrict__ eps_b, const float *__restrict__ z_b, Workspace ws,
@@ -768,6 +841,9 @@ __global__ void __launch_bounds__(kFastThreads) bm_forward_fast_kernel(
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
     gp_forward_fast<M, DIN, DH, 1>(g, xin, xt, k, a, fm, fv);
+    if constexpr (SAVE) {
+      if (live) SavedEval<G::MP, DH>::store(ws.KAb, (size_t)ch.run * D.T + t, np, nl, k, a, fm, fv);
+    }
     const bool write = writer_run(t, D.R) == ch.run;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
@@ -786,8 +862,8 @@ __global__ void __launch_bounds__(kFastThreads) bm_forward_fast_kernel(
 }
 
 // =====================================================================================
-template <int DX, int DU, int DY, int M>
-__global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
+template <int DX, int DU, int DY, int M, bool SAVE>
+__global__ void __launch_bounds__(kFastThreads, (SAVE && DX <= 4) ? 4 : 1) fw_forward_fast_kernel(
     Dims D, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ vyg, const float *__restrict__ u,
     const float *__restrict__ y, const float *__restrict__ eps_f, Workspace ws, float *__restrict__ part_out) {
   constexpr int DH = DX - DY, DIN = DX + DU;
@@ -844,6 +920,9 @@ __global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
     load_ytil(t + 1, yt);
     const float e = eps_f[(size_t)t * D.n_local + nr];
     gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
+    if constexpr (SAVE) {
+      if (live) SavedEval<G::MP, DX>::store(ws.KAf, (size_t)t, np, nl, k, a, fm, fv);
+    }
     const bool do_cond = D.condition || (t < D.R - 1);
     fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, xn, kl);
 #pragma unroll
@@ -861,7 +940,7 @@ __global__ void __launch_bounds__(kFastThreads) fw_forward_fast_kernel(
 // Reverse kernels: persistent CTAs; every WARP writes its own partial slot
 // [tile accumulators | L_j, sum w, sum G, var_x_bar, var_y_bar].
 // =====================================================================================
-template <int DX, int DU, int DY, int M>
+template <int DX, int DU, int DY, int M, bool SAVED>
 __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) fw_reverse_fast_kernel(
     Dims D, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ vyg, const float *__restrict__ u,
     const float *__restrict__ y, const float *__restrict__ eps_f, float w_ll, float w_kl, Workspace ws,
@@ -907,7 +986,9 @@ __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) fw_reverse_
     }
     // Particle-major operands of a step (x_t, y2_{t+1}, eps_t) are fetched during the previous step's
     // accumulation phase, when few registers are live, so their HBM/L2 latency is off the critical path.
+    using SE = SavedEval<G::MP, DX>;
     float xq[DX], hq[DH], eq;
+    float4 fq[SE::NF];   // SAVED: this step's (fmean, fvar), fetched a step ahead like the other operands
     auto fetch = [&](int t) {
       const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
 #pragma unroll
@@ -916,6 +997,7 @@ __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) fw_reverse_
 #pragma unroll
       for (int j = 0; j < DH; ++j) hq[j] = D.half ? 0.f : Hp[j * np];
       eq = eps_f[(size_t)t * D.n_local + nr];
+      if constexpr (SAVED) SE::load_f(ws.KAf, (size_t)t, np, nr, fq);
     };
     if (D.T >= 2) fetch(D.T - 2);
 #pragma unroll 1
@@ -934,7 +1016,13 @@ __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) fw_reverse_
 #pragma unroll
       for (int j = 0; j < DH; ++j) yt[DY + j] = hq[j];
       const float e = eq;
-      gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
+      if constexpr (SAVED) {      // the evaluation the forward kernel left behind (k, a first: they are used last)
+        SE::load_ka(ws.KAf, (size_t)t, np, nr, k, a);
+        SE::unpack_f(fq, fm, fv);
+        gp_scale_input<M, DIN, DX, 0>(g, xin, xt);
+      } else {
+        gp_forward_fast<M, DIN, DX, 0>(g, xin, xt, k, a, fm, fv);
+      }
       const bool do_cond = D.condition || (t < D.R - 1);
       float fmb[DX], fvb[DX], ytb[DX];
       fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
@@ -987,7 +1075,7 @@ __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) fw_reverse_
   }
 }
 
-template <int DX, int DU, int DY, int M>
+template <int DX, int DU, int DY, int M, bool SAVED>
 __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) bm_reverse_fast_kernel(
     Dims D, ChainTable chains, GpDev gp, const float *__restrict__ vxg, const float *__restrict__ u,
     const float *__restrict__ y, const float *__restrict__ eps_b, const float *__restrict__ z_b, float w_en,
@@ -1031,8 +1119,11 @@ __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) bm_reverse_
     for (int j = 0; j < DH; ++j) hb[j] = 0.f;
     // Particle-major operands of a step (message state, eps, adjoint of y2) are fetched during the previous
     // step's accumulation phase, when few registers are live.
+    using SE = SavedEval<G::MP, DH>;
     float hq[DH], yq[DH], eq;
+    float4 fq[SE::NF];
     auto fetch = [&](int t) {
+      if constexpr (SAVED) SE::load_f(ws.KAb, (size_t)ch.run * D.T + t, np, nr, fq);
       if (t == ch.t_hi) {
         const float z = (ch.init == 1) ? z_b[((size_t)ch.run * D.T + t) * D.n_local + nr] : 0.f;
 #pragma unroll
@@ -1062,7 +1153,13 @@ __global__ void __launch_bounds__(kFastThreads, rev_minblocks<DX>()) bm_reverse_
 #pragma unroll
       for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
       const float e = eq;
-      gp_forward_fast<M, DIN, DH, 1>(g, xin, xt, k, a, fm, fv);
+      if constexpr (SAVED) {
+        SE::load_ka(ws.KAb, (size_t)ch.run * D.T + t, np, nr, k, a);
+        SE::unpack_f(fq, fm, fv);
+        gp_scale_input<M, DIN, DH, 1>(g, xin, xt);
+      } else {
+        gp_forward_fast<M, DIN, DH, 1>(g, xin, xt, k, a, fm, fv);
+      }
       const bool write = writer_run(t, D.R) == ch.run;
       float ob[DH], fvb[DH];
 #pragma unroll

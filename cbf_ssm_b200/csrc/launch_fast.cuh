@@ -43,57 +43,88 @@ struct LaunchFast {
                                    cudaMemcpyDeviceToDevice, st);
   }
 
+  template <bool SAVE>
+  static cudaError_t bm_forward_t(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
+                                  const float *y, const float *eps_b, const float *z_b, Workspace ws,
+                                  float *part_out, cudaStream_t st) {
+    const size_t smem = smem_bytes(M, 0);
+    cudaError_t e = prep(bm_forward_fast_kernel<DX, DU, DY, M, SAVE>, smem);
+    if (e != cudaSuccess) return e;
+    if ((e = load_const(1, gp, DH, ws.cpack + kConstFloats, st)) != cudaSuccess) return e;
+    dim3 grid(ceil_div(D.n_local, kFastThreads), ct.count);
+    bm_forward_fast_kernel<DX, DU, DY, M, SAVE><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out); cbf_note_launch();
+    return cudaGetLastError();
+  }
   static cudaError_t bm_forward(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
                                 const float *y, const float *eps_b, const float *z_b, Workspace ws,
                                 float *part_out, cudaStream_t st) {
     if (ct.count == 0) return cudaSuccess;
-    const size_t smem = smem_bytes(M, 0);
-    cudaError_t e = prep(bm_forward_fast_kernel<DX, DU, DY, M>, smem);
-    if (e != cudaSuccess) return e;
-    if ((e = load_const(1, gp, DH, ws.cpack + kConstFloats, st)) != cudaSuccess) return e;
-    dim3 grid(ceil_div(D.n_local, kFastThreads), ct.count);
-    bm_forward_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out); cbf_note_launch();
-    return cudaGetLastError();
+    return ws.KAb != nullptr ? bm_forward_t<true>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out, st)
+                             : bm_forward_t<false>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out, st);
   }
 
-  static cudaError_t fw_forward(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
-                                const float *y, const float *eps_f, Workspace ws, float *part_out,
-                                cudaStream_t st) {
+  template <bool SAVE>
+  static cudaError_t fw_forward_t(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
+                                  const float *y, const float *eps_f, Workspace ws, float *part_out,
+                                  cudaStream_t st) {
     const size_t smem = smem_bytes(M, 1);
-    cudaError_t e = prep(fw_forward_fast_kernel<DX, DU, DY, M>, smem);
+    cudaError_t e = prep(fw_forward_fast_kernel<DX, DU, DY, M, SAVE>, smem);
     if (e != cudaSuccess) return e;
     if ((e = load_const(0, gp, DX, ws.cpack, st)) != cudaSuccess) return e;
-    fw_forward_fast_kernel<DX, DU, DY, M><<<ceil_div(D.n_local, kFastThreads), kFastThreads, smem, st>>>(
+    fw_forward_fast_kernel<DX, DU, DY, M, SAVE><<<ceil_div(D.n_local, kFastThreads), kFastThreads, smem, st>>>(
         D, gp, vx, vy, u, y, eps_f, ws, part_out); cbf_note_launch();
     return cudaGetLastError();
   }
+  static cudaError_t fw_forward(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
+                                const float *y, const float *eps_f, Workspace ws, float *part_out,
+                                cudaStream_t st) {
+    return ws.KAf != nullptr ? fw_forward_t<true>(D, gp, vx, vy, u, y, eps_f, ws, part_out, st)
+                             : fw_forward_t<false>(D, gp, vx, vy, u, y, eps_f, ws, part_out, st);
+  }
 
-  static cudaError_t fw_reverse(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
-                                const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
-                                float *part_out, int grid, cudaStream_t st) {
+  // saved-evaluation planes per evaluation slot (common.cuh Workspace::KAf / KAb), float4 units per particle
+  static int saved_planes(int which) { return which == 0 ? SavedEval<Gf::MP, DX>::NPL : SavedEval<Gb::MP, DH>::NPL; }
+
+  template <bool SAVED>
+  static cudaError_t fw_reverse_t(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
+                                  const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
+                                  float *part_out, int grid, cudaStream_t st) {
     const size_t smem = smem_bytes(M, 2);
-    cudaError_t e = prep(fw_reverse_fast_kernel<DX, DU, DY, M>, smem);
+    cudaError_t e = prep(fw_reverse_fast_kernel<DX, DU, DY, M, SAVED>, smem);
     if (e != cudaSuccess) return e;
     if ((e = load_const(0, gp, DX, ws.cpack, st)) != cudaSuccess) return e;
     AccLayout Lf, Lb;
     layouts(M, &Lf, &Lb);
-    fw_reverse_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws,
-                                                                           part_out, Lf.slot()); cbf_note_launch();
+    fw_reverse_fast_kernel<DX, DU, DY, M, SAVED><<<grid, kFastThreads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws,
+                                                                                  part_out, Lf.slot()); cbf_note_launch();
     return cudaGetLastError();
   }
-
-  static cudaError_t bm_reverse(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
-                                const float *y, const float *eps_b, const float *z_b, float w_en, Workspace ws,
+  static cudaError_t fw_reverse(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
+                                const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
                                 float *part_out, int grid, cudaStream_t st) {
+    return ws.KAf != nullptr ? fw_reverse_t<true>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, part_out, grid, st)
+                             : fw_reverse_t<false>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, part_out, grid, st);
+  }
+
+  template <bool SAVED>
+  static cudaError_t bm_reverse_t(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
+                                  const float *y, const float *eps_b, const float *z_b, float w_en, Workspace ws,
+                                  float *part_out, int grid, cudaStream_t st) {
     const size_t smem = smem_bytes(M, 3);
-    cudaError_t e = prep(bm_reverse_fast_kernel<DX, DU, DY, M>, smem);
+    cudaError_t e = prep(bm_reverse_fast_kernel<DX, DU, DY, M, SAVED>, smem);
     if (e != cudaSuccess) return e;
     if ((e = load_const(1, gp, DH, ws.cpack + kConstFloats, st)) != cudaSuccess) return e;
     AccLayout Lf, Lb;
     layouts(M, &Lf, &Lb);
-    bm_reverse_fast_kernel<DX, DU, DY, M><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws,
-                                                                           part_out, Lb.slot()); cbf_note_launch();
+    bm_reverse_fast_kernel<DX, DU, DY, M, SAVED><<<grid, kFastThreads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws,
+                                                                                  part_out, Lb.slot()); cbf_note_launch();
     return cudaGetLastError();
+  }
+  static cudaError_t bm_reverse(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
+                                const float *y, const float *eps_b, const float *z_b, float w_en, Workspace ws,
+                                float *part_out, int grid, cudaStream_t st) {
+    return ws.KAb != nullptr ? bm_reverse_t<true>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, part_out, grid, st)
+                             : bm_reverse_t<false>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, part_out, grid, st);
   }
 
   static int occupancy(int, int which) {
@@ -101,11 +132,11 @@ struct LaunchFast {
     int nb = 0;
     cudaError_t e;
     if (which == 2) {
-      if (prep(fw_reverse_fast_kernel<DX, DU, DY, M>, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fw_reverse_fast_kernel<DX, DU, DY, M>, kFastThreads, smem);
+      if (prep(fw_reverse_fast_kernel<DX, DU, DY, M, false>, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fw_reverse_fast_kernel<DX, DU, DY, M, false>, kFastThreads, smem);
     } else {
-      if (prep(bm_reverse_fast_kernel<DX, DU, DY, M>, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bm_reverse_fast_kernel<DX, DU, DY, M>, kFastThreads, smem);
+      if (prep(bm_reverse_fast_kernel<DX, DU, DY, M, false>, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bm_reverse_fast_kernel<DX, DU, DY, M, false>, kFastThreads, smem);
     }
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return nb;
@@ -129,6 +160,7 @@ DimOps make_fast_ops() {
   o.smem_bytes = &L::smem_bytes;
   o.occupancy = &L::occupancy;
   o.layouts = &L::layouts;
+  o.saved_planes = &L::saved_planes;
   o.slots_per_cta = kFastWarps;
   o.particles_per_cta = kFastThreads;
   o.fixed_M = M;

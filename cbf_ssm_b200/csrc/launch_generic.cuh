@@ -127,6 +127,7 @@ DimOps make_ops() {
   o.smem_bytes = &Launch<DX, DU, DY>::smem_bytes;
   o.occupancy = &Launch<DX, DU, DY>::occupancy;
   o.layouts = &Launch<DX, DU, DY>::layouts;
+  o.saved_planes = nullptr;
   o.slots_per_cta = 1;
   o.particles_per_cta = kNP;
   o.fixed_M = 0;

@@ -221,12 +221,12 @@ class ElboEngine:
         self._ev_join.record(self._side)
         main.wait_event(self._ev_join)
 
-    def make_shape(self, B, T, condition=True, n_offset=0, n_local=None):
+    def make_shape(self, B, T, condition=True, n_offset=0, n_local=None, predict_only=False):
         d = self.dims
         n_local = B * d.samples - n_offset if n_local is None else n_local
         return cbf_shape(B, d.samples, T, d.ind_pnt_num, d.dim_x, d.dim_u, d.dim_y, d.recog_len,
                          1 if condition else 0, n_offset, n_local, float(d.k_factor),
-                         int(self.flags) | (32 if d.half else 0))
+                         int(self.flags) | (32 if d.half else 0) | (256 if predict_only and not condition else 0))
 
     def _ensure_workspace(self, shape):
         # The plan the library binds onto the buffer depends on everything in ``shape`` (flags select the kernel
@@ -267,13 +267,16 @@ class ElboEngine:
                                           ptr(g.Z), ptr(g.ell), ptr(g.sig2), ptr(g.P), ptr(g.alpha), ptr(g.S),
                                           ptr(g.kl), ptr(g.state), s2))
 
-    def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True, x0=None):
+    def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True, x0=None,
+                predict_only=False):
         """u [B,T,du], y [B,T,dy] float32 device tensors; draws float32 device tensors
         eps_b/z_b [2,T,n_local], eps_f [T-1,n_local].  Returns a dict of 0-d device
         tensors (this shard's loglik/kl_x/entropy; loss is global when a group is set
         only after ``backward``)."""
         B, T, _ = u.shape
-        shape = self.make_shape(B, T, condition, n_offset, n_local)
+        # predict_only: only the prediction outputs will be read (no loss / entropy / y_tilde / backward): with
+        # condition False the library then runs just the message chain the free-running rollout needs
+        shape = self.make_shape(B, T, condition, n_offset, n_local, predict_only)
         self._ensure_workspace(shape)
         if run_prologue:
             self.prologue()

@@ -175,7 +175,11 @@ class CBFSSM(BaseModel):
         ud.record_stream(main)
         yd.record_stream(main)
         n0 = n0_rel
-        out = eng.forward(ud, yd, eb, zb, ef, condition=condition, n_offset=n0, n_local=nl)
+        # Outputs.create_all fetches only prediction handles with condition False (outputs.py:68-71,128-130): then
+        # the message is needed for t < recog_len only
+        pred_only = (not condition) and all(n in ("pred_mean", "pred_var", "internal_mean", "internal_var", "mse", "sde",
+                                                  "x_final", "y_final") or n.startswith("var:") for n in names)
+        out = eng.forward(ud, yd, eb, zb, ef, condition=condition, n_offset=n0, n_local=nl, predict_only=pred_only)
         if "train" in names:
             eng.backward()                   # all-reduces gradient + terms when sharded
             out = eng.loss_terms(eng.terms)

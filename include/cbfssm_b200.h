@@ -78,6 +78,12 @@ typedef struct cbf_shape {
  * sets whose cond(K_zz) is beyond float32's reach (crowded inducing points), where the float32 paths are
  * accuracy-limited.  Needs cbf_gp.state. */
 #define CBF_FLAG_FP64 128
+/* Prediction only (cbfssm/outputs/outputs.py:68-71,128-130: pred_mean / pred_var with condition = False): with
+ * condition == 0 the rollout reads y2[t] only for t < R (cbfssm.py:227-228), so cbf_elbo_forward runs just the
+ * message chain(s) that write those steps -- <= 2R message steps instead of ~2T.  terms[2] (entropy) then covers
+ * only those steps and y_tilde beyond t = R-1 is not produced; cbf_elbo_backward refuses the flag.  No effect
+ * when condition != 0. */
+#define CBF_FLAG_PREDICT_ONLY 256
 
 
 /* Kernel-level operands of one sparse GP (gp_tf.py:103-130), float32, produced by

@@ -290,3 +290,50 @@ def test_bench_b200_arm_prints_the_contract_line():
     assert "workload" in line["config"] and "model" not in line["config"]
     x = line["extra"]["robomove_m20"]                  # BASELINE.json configs[1] in the same line
     assert x["config"]["M"] == 20 and x["value"] > 0 and x["roofline"]["bound"] == "fp32_simt" and 0 < x["roofline"]["frac"] < 1
+
+
+@pytest.mark.parametrize("M", [20, 100], ids=["register_m20", "tensor_m100"])
+def test_predict_only_skips_dead_message_work_and_changes_nothing(M):
+    """Free-running prediction (condition=False) reads y2[t] only for t < recog_len (cbfssm.py:227-228): with
+    CBF_FLAG_PREDICT_ONLY the library runs one message chain of <= 2R steps instead of ~2T, and pred_mean / pred_var
+    / x_final are bit-identical to the full evaluation."""
+    eng = _engine(M=M, S=16, R=5)
+    B, T = 3, 64
+    u, y, eb, zb, ef = _inputs(eng, B, T, seed=4)
+    outs = []
+    for po in (False, True):
+        n0 = eng.launches
+        eng.forward(u, y, eb, zb, ef, False, predict_only=po)
+        xf, _ = eng.export_states(y)
+        pm, pv = eng.moments(xf, eng.dims.dim_y, eng.var_y)
+        torch.cuda.synchronize()
+        outs.append((xf.clone(), pm.clone(), pv.clone(), float(eng.terms[2])))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert outs[1][3] != outs[0][3]                     # the entropy term covers only the steps that were run
+    with pytest.raises(Exception):
+        eng.backward()                                  # a predict-only forward cannot be differentiated
+    # the public API takes the short cut by itself when only prediction handles are fetched
+    from cbf_ssm_b200.engine import ElboEngine
+    eng.forward(u, y, eb, zb, ef, True, predict_only=True)   # no effect with condition=True: full message, backward allowed
+    eng.backward()
+
+
+def test_register_path_saved_evaluations_equal_recomputation(monkeypatch):
+    """The register path keeps (k, a, fmean, fvar) of every GP evaluation for the reverse pass when the extra
+    workspace fits its budget, and recomputes them otherwise: both give bit-identical gradients."""
+    outs = []
+    for budget in ("0", None):
+        if budget is None:
+            monkeypatch.delenv("CBFSSM_B200_SAVE_EVAL_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("CBFSSM_B200_SAVE_EVAL_BYTES", budget)
+        eng = _engine()
+        eng.flags = 4
+        B, T = 7, 120
+        u, y, eb, zb, ef = _inputs(eng, B, T, seed=2)
+        eng.forward(u, y, eb, zb, ef, True)
+        eng.backward()
+        torch.cuda.synchronize()
+        outs.append((eng._gflat.clone(), eng.terms.clone(), int(eng._ws.numel())))
+    assert outs[1][2] > outs[0][2]                       # the saved evaluations live in the workspace
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
