@@ -133,27 +133,41 @@ __device__ __forceinline__ void split_h(float x, __half &h1, __half &h2) {
 // and named barrier and runs independently; the tiles share P1/P2 and the small tables.  NT = 2 is used
 // where one tile's CTA is too large for two CTAs per SM (D >= 8 at M = 100: 11-22 KB of tables), which
 // restores 8 warps per SM.
-template <int DIN, int DOUT, bool REV = false, int MC_ = 0, int NT_ = 1>
+//
+// NG > 1 (latency variant, NT = 1 only): NG x 128 threads work on ONE particle tile, thread (g, lane) handling the
+// 16-row chunks cc = g, g + NG, ... of particle `lane`'s M-vectors (warps w and w + 4 read the same TMEM lane
+// quarter).  Per-particle partial sums cross the groups through the small exchange buffer `xch` in a fixed order, so
+// all NG threads of a particle carry bit-identical per-particle state.  It shortens the serial chain of one time
+// step by ~NG and is used when the launch has too few particle tiles to fill the SMs anyway (small minibatches,
+// strong scaling, prediction of one long sequence).
+template <int DIN, int DOUT, bool REV = false, int MC_ = 0, int NT_ = 1, int NG_ = 1>
 struct TcCtx {
   static constexpr int NT = NT_;
+  static constexpr int NG = NG_;
+  static_assert(NG == 1 || NT == 1, "the M-split variant runs one particle tile per CTA");
+  static constexpr int XV = 1 + (2 * DOUT + 2) + DIN;   // exchange values per (group, particle): d2min | q, amax, fm, fv | x_bar
   static constexpr int MC = MC_;     // compile-time M (0: runtime) -- lets the M loops unroll and drop their guards
   static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   static constexpr uint32_t TMEM_COLS = REV ? 256u : 128u;
   __half *P1, *P2, *K1, *K2, *B1, *B2;
   const float *Zt, *al, *Sm, *il;
+  float *xch;           // (NG > 1) [NG][XV][128] partial sums between the groups of a particle
   uint32_t bar, tmem, tmem_base, idesc;
   uint32_t phase;
   int M, MP;
-  int tile_, tl_;       // (NT > 1) particle tile of this thread within the CTA, lane (= TMEM lane, operand row) in the tile
+  int tile_, tl_;       // (NT > 1 or NG > 1) particle tile / group of this thread within the CTA, lane (= TMEM lane, operand row) in the tile
   __device__ __forceinline__ int tile_id() const { return NT == 1 ? 0 : tile_; }
-  __device__ __forceinline__ int lane_id() const { return NT == 1 ? (int)threadIdx.x : tl_; }
+  __device__ __forceinline__ int grp() const { return NG == 1 ? 0 : tile_; }
+  __device__ __forceinline__ int lane_id() const { return (NT == 1 && NG == 1) ? (int)threadIdx.x : tl_; }
+  __device__ __forceinline__ float *xslot(int g, int v) const { return xch + ((size_t)(g * XV + v)) * kTcThreads + tl_; }
   float sig2, pscale;   // P = pscale * P'
   float smax[DOUT];     // max_m S_md (bound used to scale b in the reverse pass)
 
   static size_t bytes(int M) {
     const int MP = round_up(M, 16);
     return (size_t)2 * MP * MP * 2 + (size_t)NT * 2 * kTcThreads * MP * 2 +
-           sizeof(float) * ((size_t)MP * (DINP + 2 * DOUTP) + DINP + 4) + 64;
+           sizeof(float) * ((size_t)MP * (DINP + 2 * DOUTP) + DINP + 4) + 64 +
+           (NG > 1 ? sizeof(float) * (size_t)NG * XV * kTcThreads : 0);
   }
 
   // Carve + fill (all threads).  Allocates TMEM (warp 0) and initialises the mbarrier.
@@ -162,7 +176,7 @@ struct TcCtx {
     P1 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
     P2 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
     tile_ = threadIdx.x / kTcThreads; tl_ = threadIdx.x % kTcThreads;
-    const int tile = tile_id();
+    const int tile = tile_id();     // 0 in the M-split variant: all groups share one tile's buffers
     K1 = reinterpret_cast<__half *>(base) + (size_t)(2 * tile) * kTcThreads * MP;
     K2 = K1 + (size_t)kTcThreads * MP;
     base += (size_t)NT * 2 * kTcThreads * MP * 2;
@@ -178,6 +192,9 @@ struct TcCtx {
     float *iw = reinterpret_cast<float *>(base); base += sizeof(float) * (DINP + 4);
     uint64_t *barp = reinterpret_cast<uint64_t *>(base); base += 32;   // one mbarrier per tile
     uint32_t *tmemp = reinterpret_cast<uint32_t *>(base); base += 16;
+    base += 16;
+    xch = reinterpret_cast<float *>(base);
+    if (NG > 1) base += sizeof(float) * (size_t)NG * XV * kTcThreads;
     const int tid = threadIdx.x, nt = blockDim.x;
     // scale of P: |P / 2^e| <= 1024
     float mx = 0.f;
@@ -261,7 +278,7 @@ __device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __h
   async_proxy_fence();
   tc_fence_before();
   if (Ctx::NT == 1) __syncthreads(); else tile_sync(c.tile_id());
-  if (c.lane_id() == 0) {
+  if (c.lane_id() == 0 && c.grp() == 0) {
     tc_fence_after();
     const uint32_t lboA = kTcThreads * 16, lboB = c.MP * 16;
     const uint32_t a1 = smem_u32(a1p), a2 = smem_u32(a2p), b1 = smem_u32(c.P1), b2 = smem_u32(c.P2);
@@ -390,13 +407,16 @@ struct TcOut {
 // kout (optional): operand-tile column receiving k' for the outer-product GEMMs.
 // amax: max_m |a''_m| of this particle's normalised accumulator row (scales b in the reverse pass);
 // kscale: the particle's normalisation, k' = kscale * k''.
+// With NG groups (Ctx::NG > 1) a thread handles the 16-row chunks cc = grp, grp + NG, ...; every result
+// (fm, fv, amax, kscale) is the same in all NG threads of a particle.
 template <class Ctx, int DIN, int DOUT>
 __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], float (&xt)[(DIN + 3) / 4 * 4],
                                               float (&fm)[DOUT], float (&fv)[DOUT], const TcOut *kout,
                                               float &amax, float &kscale) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
-  constexpr int MC = Ctx::MC;
-  const int t = c.lane_id(), M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
+  constexpr int MC = Ctx::MC, NG = Ctx::NG;
+  const int t = c.lane_id(), g0 = c.grp(), M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
+  (void)M;
   {
     float il[DINP];
     ld_row<DINP>(c.il, il);
@@ -416,8 +436,11 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   // distances (float32) in the thread's own K1/K2 slots and finds their minimum, pass 2 forms
   // k'' = exp(-(d^2 - d^2_min)/2) in (0,1] (max exactly 1), splits and overwrites.  k' = kscale * k''.
   float d2min = 3.0e38f;
-#pragma unroll(MC ? 2 : 1)
-  for (int ch = 0; ch < MP / 8; ++ch) {
+#pragma unroll 1
+  for (int cc = g0; cc < MP / 16; cc += NG)
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {   // 8-row chunks 2cc, 2cc+1 of the own 16-row chunks cc
+    const int ch = 2 * cc + hh;
     float dv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -438,9 +461,18 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
     *reinterpret_cast<float4 *>(c.K1 + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
     *reinterpret_cast<float4 *>(c.K2 + off) = make_float4(dv[4], dv[5], dv[6], dv[7]);
   }
+  if (NG > 1) {   // the particle's minimum over all groups
+    *c.xslot(g0, 0) = d2min;
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < NG; ++g) d2min = fminf(d2min, *c.xslot(g, 0));
+  }
   kscale = fast_exp2(kNegHalfLog2e * d2min);
-#pragma unroll(MC ? 2 : 1)
-  for (int ch = 0; ch < MP / 8; ++ch) {
+#pragma unroll 1
+  for (int cc = g0; cc < MP / 16; cc += NG)
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int ch = 2 * cc + hh;
     const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
     const float4 da = *reinterpret_cast<const float4 *>(c.K1 + off), db = *reinterpret_cast<const float4 *>(c.K2 + off);
     const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
@@ -471,15 +503,15 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   amax = 0.f;
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
   uint32_t ra[16];
-  tmem_ld16_issue(trow, ra);
+  if (g0 < MP / 16) tmem_ld16_issue(trow + g0 * 16, ra);
 #pragma unroll(MC ? kTcChunkUnroll : 1)
-  for (int cc = 0; cc < MP / 16; ++cc) {
+  for (int cc = g0; cc < MP / 16; cc += NG) {
     float a[16], kp[16];
     tc_read_row16(c.K1, c.K2, t, cc, kp);
     tmem_ld_wait(ra);
 #pragma unroll
     for (int e = 0; e < 16; ++e) a[e] = __uint_as_float(ra[e]);
-    if (cc + 1 < MP / 16) tmem_ld16_issue(trow + (cc + 1) * 16, ra);   // next chunk in flight during this one's math
+    if (cc + NG < MP / 16) tmem_ld16_issue(trow + (cc + NG) * 16, ra);   // next chunk in flight during this one's math
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
@@ -501,6 +533,23 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
     fm[2 * d] = m0; fv[2 * d] = v0;
     if (2 * d + 1 < DOUT) { fm[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = m1; fv[2 * d + 1 < DOUT ? 2 * d + 1 : 0] = v1; }
   }
+  if (NG > 1) {   // partial sums of the groups, added in group order by every thread of the particle
+    *c.xslot(g0, 1) = q;
+    *c.xslot(g0, 2) = amax;
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) { *c.xslot(g0, 3 + d) = fm[d]; *c.xslot(g0, 3 + DOUT + d) = fv[d]; }
+    __syncthreads();
+    q = 0.f; amax = 0.f;
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) { fm[d] = 0.f; fv[d] = 0.f; }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      q += *c.xslot(g, 1);
+      amax = fmaxf(amax, *c.xslot(g, 2));
+#pragma unroll
+      for (int d = 0; d < DOUT; ++d) { fm[d] += *c.xslot(g, 3 + d); fv[d] += *c.xslot(g, 3 + DOUT + d); }
+    }
+  }
   // q, fv, amax were formed from the normalised k'' and a'' = P' k''; undo the per-particle scale
   const float s4 = c.sig2 * c.sig2, ps = c.pscale, k2 = kscale * kscale;
 #pragma unroll
@@ -513,26 +562,29 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 
 // Reverse of one GP evaluation (SURVEY 8a note 4) on the tile; follows gp_forward_tc of the same step
 // (K1/K2 and the accumulator D1 still hold k' and a').  gm/gv: adjoints of (fmean, fvar).
+// NG > 1: Lacc and sw receive this thread's chunks only (they are summed over all threads at the end of the
+// kernel); sG is added by group 0; xinb is the full sum in every thread.
 template <class Ctx, int DIN, int DOUT, int NEED>
 __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3) / 4 * 4], const float (&gm)[DOUT],
                                               const float (&gv)[DOUT], float amax, float kscale, bool live,
                                               const TcOut &o, float (&xinb)[NEED], float (&Lacc)[DIN], float &sw,
                                               float &sG) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
-  constexpr int MC = Ctx::MC;
-  const int t = c.lane_id(), M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
+  constexpr int MC = Ctx::MC, NG = Ctx::NG;
+  const int t = c.lane_id(), g0 = c.grp(), M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
+  (void)M;
   const float ps = c.pscale, sig2 = c.sig2;
   const float ascale = ps * sig2 * kscale;      // a = ascale * a'' (a'' = P' k'' is what D1 holds)
   float Gs = 0.f, cbound = 0.f;
 #pragma unroll
   for (int d = 0; d < DOUT; ++d) { Gs += gv[d]; cbound += fabsf(gv[d]) * c.smax[d]; }
-  sG += Gs;
+  if (g0 == 0) sG += Gs;
   // per-particle power-of-two scale so that |b''| = |a'' c| * 2^-e <= 1  (amax is of the normalised a'')
   int e2 = 0;
   frexpf(fmaxf(amax * cbound, 1e-30f), &e2);
   const float bsc = ldexpf(1.f, -e2), binv = ldexpf(1.f, e2);
   const uint32_t trow1 = c.tmem + ((uint32_t)(t & ~31) << 16), trow2 = trow1 + 128;
-  if (live) {
+  if (live && g0 == 0) {
     o.template put_vec<DOUT>(o.bGm, gm);
     o.template put_vec<DOUT>(o.bGv, gv);
     float x1[DIN + 1];
@@ -543,14 +595,14 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   }
   // ---- b'' = a' (S gv) 2^-e -> fp16 split rows of B ----
   uint32_t ra1[16];
-  tmem_ld16_issue(trow1, ra1);
+  if (g0 < MP / 16) tmem_ld16_issue(trow1 + g0 * 16, ra1);
 #pragma unroll(MC ? kTcChunkUnroll : 1)
-  for (int cc = 0; cc < MP / 16; ++cc) {
+  for (int cc = g0; cc < MP / 16; cc += NG) {
     float a[16];
     tmem_ld_wait(ra1);
 #pragma unroll
     for (int e = 0; e < 16; ++e) a[e] = __uint_as_float(ra1[e]);
-    if (cc + 1 < MP / 16) tmem_ld16_issue(trow1 + (cc + 1) * 16, ra1);
+    if (cc + NG < MP / 16) tmem_ld16_issue(trow1 + (cc + NG) * 16, ra1);
     float bv[16], a2[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -578,7 +630,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   }
   tc_fence_before();
   uint4 kq[4];   // raw hi/lo segments of two row-blocks of k' (one 16-row chunk), fetched one chunk ahead
-  o.get8_raw(o.bK, live, kq);
+  o.get8_raw(o.bK + 2 * g0, live, kq);
   // ---- D2 = B P' ----
   tc_contract(c, c.B1, c.B2, c.tmem + 128);
   // ---- k_bar = alpha gm + 2 P b - 2 G a ; w = k_bar k ; a_bar = 2 b - G k ----
@@ -591,7 +643,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 #pragma unroll
   for (int j = 0; j < N2; ++j) xs2[j] = 0ull;
 #pragma unroll(MC ? kTcChunkUnroll : 1)
-  for (int cc = 0; cc < MP / 16; ++cc) {
+  for (int cc = g0; cc < MP / 16; cc += NG) {
     float pb[16], a[16], kp[16], bb[16];
     {
       uint32_t rp[16], ra[16];
@@ -599,7 +651,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       tmem_ld16_issue(trow1 + cc * 16, ra);
       // true k' of this chunk was fetched one iteration ahead; fetch the next chunk's now
       const uint4 c0 = kq[0], c1 = kq[1], c2 = kq[2], c3 = kq[3];
-      if (cc + 1 < MP / 16) o.get8_raw(o.bK + 2 * cc + 2, live, kq);
+      if (cc + NG < MP / 16) o.get8_raw(o.bK + 2 * (cc + NG), live, kq);
       tc_read_row16(c.B1, c.B2, t, cc, bb);
       {
         float k0[8], k1[8];
@@ -657,41 +709,58 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     if (2 * j + 1 < DIN) Lacc[2 * j + 1 < DIN ? 2 * j + 1 : 0] += l1;
   }
   {
+    float xs[2 * N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) unpack2(xs2[j], xs[2 * j], xs[2 * j + 1]);
+    if (NG > 1) {   // x_bar heads the next step's dependency chain: every thread of the particle needs the full sum
+      constexpr int X0 = 3 + 2 * DOUT;
+#pragma unroll
+      for (int j = 0; j < NEED; ++j) *c.xslot(g0, X0 + j) = xs[j];
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < NEED; ++j) {
+        float v = 0.f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) v += *c.xslot(g, X0 + j);
+        xs[j] = v;
+      }
+    }
     float il[DINP];
     ld_row<DINP>(c.il, il);
 #pragma unroll
-    for (int j = 0; j < N2; ++j) {
-      float s0, s1;
-      unpack2(xs2[j], s0, s1);
-      xinb[2 * j] = -s0 * il[2 * j];
-      if (2 * j + 1 < NEED) xinb[2 * j + 1 < NEED ? 2 * j + 1 : 0] = -s1 * il[2 * j + 1];
-    }
+    for (int j = 0; j < NEED; ++j) xinb[j] = -xs[j] * il[j];
   }
   tc_fence_before();
 }
 
-// Sum COUNT per-thread floats over one particle tile (128 threads); the tile's thread 0 writes out[0..COUNT)
-// unless out is null.  scratch: 4 * COUNT floats owned by the tile.
-template <int COUNT, int NT>
+// Sum COUNT per-thread floats over one particle tile (128 threads x NG groups); the tile's thread 0 writes
+// out[0..COUNT) unless out is null.  scratch: 4 * NG * COUNT floats owned by the tile.
+template <int COUNT, int NT, int NG = 1>
 __device__ __forceinline__ void tile_sum_store(const float (&vals)[COUNT], float *scratch, float *out, int tile, int tl) {
-  const int lane = tl & 31, warp = tl >> 5;
+  constexpr int NW = 4 * NG;
+  const int lane = tl & 31, warp = (NG == 1) ? (tl >> 5) : (int)(threadIdx.x >> 5);
   if (NT == 1) __syncthreads(); else tile_sync(tile);
 #pragma unroll
   for (int i = 0; i < COUNT; ++i) {
     float v = vals[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) scratch[i * 4 + warp] = v;
+    if (lane == 0) scratch[i * NW + warp] = v;
   }
   if (NT == 1) __syncthreads(); else tile_sync(tile);
-  if (tl == 0 && out != nullptr) {
-    for (int i = 0; i < COUNT; ++i) out[i] = scratch[i * 4] + scratch[i * 4 + 1] + scratch[i * 4 + 2] + scratch[i * 4 + 3];
+  if (tl == 0 && (NG == 1 || threadIdx.x == 0) && out != nullptr) {
+    for (int i = 0; i < COUNT; ++i) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sum += scratch[i * NW + w];
+      out[i] = sum;
+    }
   }
 }
 
 // =====================================================================================
-template <int DX, int DU, int DY, int MC, int NT>
-__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+template <int DX, int DU, int DY, int MC, int NT, int NG = 1>
+__global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2 : 1) bm_forward_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -700,9 +769,9 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_forward_t
                                                                    float *__restrict__ part_out) {
   constexpr int DH = DX - DY, DIN = DX + DU;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float scratch[8];
+  __shared__ float scratch[4 * NT * NG + 8];
   __shared__ float vx[16];
-  using Ctx = TcCtx<DIN, DH, false, MC, NT>;
+  using Ctx = TcCtx<DIN, DH, false, MC, NT, NG>;
   Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
   if (threadIdx.x < DX) vx[threadIdx.x] = vxg[threadIdx.x];
@@ -743,20 +812,20 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_forward_t
       h[j] = fm[j] + h[j] + e * sqrtf(f);
       if (write) ent += 0.5f * (kLog2PiE + logf(f));
     }
-    if (live) {
+    if (live && c.grp() == 0) {
       float *Hp = ws.H + (((size_t)ch.run * D.T + t) * DH) * np + nl;
 #pragma unroll
       for (int j = 0; j < DH; ++j) Hp[j * np] = h[j];
     }
   }
   c.release();
-  const float v[1] = {live ? ent : 0.f};
-  tile_sum_store<1, NT>(v, scratch + 4 * c.tile_id(), gtile < ntiles ? part_out + ((size_t)blockIdx.y * ntiles + gtile) : nullptr,
+  const float v[1] = {(live && c.grp() == 0) ? ent : 0.f};
+  tile_sum_store<1, NT, NG>(v, scratch + 4 * c.tile_id(), gtile < ntiles ? part_out + ((size_t)blockIdx.y * ntiles + gtile) : nullptr,
                         c.tile_id(), c.lane_id());
 }
 
-template <int DX, int DU, int DY, int MC, int NT>
-__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+template <int DX, int DU, int DY, int MC, int NT, int NG = 1>
+__global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2 : 1) fw_forward_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -764,9 +833,9 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_forward_t
                                                                    float *__restrict__ part_out) {
   constexpr int DH = DX - DY, DIN = DX + DU;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float scratch[NT * 4 * (DY + 1) + 8];
+  __shared__ float scratch[NT * NG * 4 * (DY + 1) + 8];
   __shared__ float vx[16], vy[16];
-  using Ctx = TcCtx<DIN, DX, false, MC, NT>;
+  using Ctx = TcCtx<DIN, DX, false, MC, NT, NG>;
   Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
   if (threadIdx.x < DX) { vx[threadIdx.x] = vxg[threadIdx.x]; vy[threadIdx.x] = vyg[threadIdx.x]; }
@@ -799,7 +868,7 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_forward_t
   }
 #pragma unroll 1
   for (int t = 0; t < D.T; ++t) {
-    if (live) {
+    if (live && c.grp() == 0) {
       float *Xp = ws.X + ((size_t)t * DX) * np + nl;
 #pragma unroll
       for (int j = 0; j < DX; ++j) Xp[j * np] = x[j];
@@ -823,11 +892,11 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_forward_t
   }
   c.release();
   sse[DY] = kl;
-  if (!live) {
+  if (!live || c.grp() != 0) {
 #pragma unroll
     for (int j = 0; j <= DY; ++j) sse[j] = 0.f;
   }
-  tile_sum_store<DY + 1, NT>(sse, scratch + 4 * (DY + 1) * c.tile_id(), gtile < ntiles ? part_out + (size_t)gtile * (DY + 1) : nullptr,
+  tile_sum_store<DY + 1, NT, NG>(sse, scratch + 4 * (DY + 1) * c.tile_id(), gtile < ntiles ? part_out + (size_t)gtile * (DY + 1) : nullptr,
                              c.tile_id(), c.lane_id());
 }
 
@@ -843,8 +912,8 @@ __device__ __forceinline__ TcOut tc_out_at(const TcMats &m, size_t col) {
 // Reverse of the forward rollout on tcgen05: one CTA = 128 particles, T-1 steps.
 // Per-CTA output: scalar sums [L_j | sum w | sum G | var_x_bar | var_y_bar] at spart[cta].
 // =====================================================================================
-template <int DX, int DU, int DY, int MC, int NT>
-__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
+template <int DX, int DU, int DY, int MC, int NT, int NG = 1>
+__global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2 : 1) fw_reverse_tc_kernel(Dims D, GpDev gp, const float *__restrict__ vxg,
                                                                    const float *__restrict__ vyg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -852,9 +921,9 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
                                                                    float w_kl, Workspace ws, TcMats mats,
                                                                    TimeWin win, float *__restrict__ spart, int nsc) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using Ctx = TcCtx<DIN, DX, true, MC, NT>;
+  using Ctx = TcCtx<DIN, DX, true, MC, NT, NG>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float scratch[NT * 4 * (DIN + 2 + 2 * DX)];
+  __shared__ float scratch[NT * NG * 4 * (DIN + 2 + 2 * DX)];
   __shared__ float vx[16], vy[16];
   Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
@@ -916,11 +985,14 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
     gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale);
     const bool do_cond = D.condition || (t < D.R - 1);
     float fmb[DX], fvb[DX], ytb[DX];
-    fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc, live);
+    fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc,
+                        live && c.grp() == 0);
     if (live) {
-      float *Yp = ws.Yb + ((size_t)(t + 1) * DH) * np + nl;
+      if (c.grp() == 0) {
+        float *Yp = ws.Yb + ((size_t)(t + 1) * DH) * np + nl;
 #pragma unroll
-      for (int j = 0; j < DH; ++j) Yp[j * np] = ytb[DY + j];
+        for (int j = 0; j < DH; ++j) Yp[j * np] = ytb[DY + j];
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < DX; ++j) { fmb[j] = 0.f; fvb[j] = 0.f; }
@@ -934,7 +1006,9 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
       xb[j] = xinb[j] + fmb[j] + lg;
     }
   }
-  if (!win.last) {
+  if (c.grp() != 0) {
+    // only group 0 stores per-particle results
+  } else if (!win.last) {
     if (live) {
 #pragma unroll
       for (int j = 0; j < DX; ++j) ws.carry_f[j * np + nl] = xb[j];
@@ -954,12 +1028,12 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) fw_reverse_t
   sc[DIN] = sw; sc[DIN + 1] = sG;
 #pragma unroll
   for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = vxacc[j]; sc[DIN + 2 + DX + j] = vyacc[j]; }
-  tile_sum_store<DIN + 2 + 2 * DX, NT>(sc, scratch + 4 * (DIN + 2 + 2 * DX) * c.tile_id(),
+  tile_sum_store<DIN + 2 + 2 * DX, NT, NG>(sc, scratch + 4 * (DIN + 2 + 2 * DX) * c.tile_id(),
                                        gtile < ntiles ? spart + (size_t)gtile * nsc : nullptr, c.tile_id(), c.lane_id());
 }
 
-template <int DX, int DU, int DY, int MC, int NT>
-__global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
+template <int DX, int DU, int DY, int MC, int NT, int NG = 1>
+__global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2 : 1) bm_reverse_tc_kernel(Dims D, ChainTable chains, GpDev gp,
                                                                    const float *__restrict__ vxg,
                                                                    const float *__restrict__ u,
                                                                    const float *__restrict__ y,
@@ -968,9 +1042,9 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_reverse_t
                                                                    Workspace ws, TcMats mats,
                                                                    float *__restrict__ spart, int nsc) {
   constexpr int DH = DX - DY, DIN = DX + DU;
-  using Ctx = TcCtx<DIN, DH, true, MC, NT>;
+  using Ctx = TcCtx<DIN, DH, true, MC, NT, NG>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float scratch[NT * 4 * (DIN + 2 + 2 * DX)];
+  __shared__ float scratch[NT * NG * 4 * (DIN + 2 + 2 * DX)];
   __shared__ float vx[16];
   Ctx c;
   c.init(smem_raw, gp, D.M, scratch);
@@ -1039,14 +1113,14 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_reverse_t
       fb += ov * e * 0.5f * rsqrtf(f);
       if (!live) { ov = 0.f; fb = 0.f; }
       ob[j] = ov; fvb[j] = fb;
-      vxacc[j] += fb;
+      if (c.grp() == 0) vxacc[j] += fb;
     }
     float xinb[DH];
     gp_reverse_tc<Ctx, DIN, DH, DH>(c, xt, ob, fvb, amax, kscale, live, o, xinb, Lacc, sw, sG);
 #pragma unroll
     for (int j = 0; j < DH; ++j) hb[j] = xinb[j] + ob[j];
   }
-  if ((ch.carry & 2) && live) {
+  if ((ch.carry & 2) && live && c.grp() == 0) {
 #pragma unroll
     for (int j = 0; j < DH; ++j) ws.carry_b[((size_t)ch.id * DH + j) * np + nl] = hb[j];
   }
@@ -1057,7 +1131,7 @@ __global__ void __launch_bounds__(NT * kTcThreads, NT == 1 ? 2 : 1) bm_reverse_t
   sc[DIN] = sw; sc[DIN + 1] = sG;
 #pragma unroll
   for (int j = 0; j < DX; ++j) { sc[DIN + 2 + j] = (j < DH) ? vxacc[j < DH ? j : 0] : 0.f; sc[DIN + 2 + DX + j] = 0.f; }
-  tile_sum_store<DIN + 2 + 2 * DX, NT>(sc, scratch + 4 * (DIN + 2 + 2 * DX) * c.tile_id(),
+  tile_sum_store<DIN + 2 + 2 * DX, NT, NG>(sc, scratch + 4 * (DIN + 2 + 2 * DX) * c.tile_id(),
                                        gtile < ntiles ? spart + ((size_t)blockIdx.y * ntiles + gtile) * nsc : nullptr,
                                        c.tile_id(), c.lane_id());
 }
@@ -1069,19 +1143,49 @@ struct LaunchTc {
   static constexpr bool kHas100 = (DX == 4 && (DU == 1 || DU == 2)) || DX == 14;
   // dims whose tables can push a one-tile CTA past two CTAs per SM: the two-tile kernels are compiled too
   static constexpr bool kDual = DX >= 8;
+  // dims with the latency variant (kSplitG threads per particle, TcCtx NG): used when a launch has fewer CTAs than
+  // the GPU has SMs, i.e. when the serial chain of a time step, not throughput, sets the kernel's duration
+  static constexpr bool kSplit = DX <= 4;
+  static constexpr int kSplitG = 2;
   static constexpr size_t kMaxDyn = 227 * 1024;
   static size_t smem_b(int M) { return TcCtx<DIN, DH>::bytes(M); }
   static size_t smem_f(int M) { return TcCtx<DIN, DX>::bytes(M); }
   static size_t smem_rb(int M) { return TcCtx<DIN, DH, true>::bytes(M); }
   static size_t smem_rf(int M) { return TcCtx<DIN, DX, true>::bytes(M); }
 
-  // Launch `k1` (one particle tile per CTA) or, when only one such CTA fits an SM and the two-tile CTA fits
-  // at all, `k2` (two tiles sharing P and the tables).  `launch(kernel, grid_x, threads, smem)` enqueues.
-  template <class K1, class K2, class F>
-  static cudaError_t pick(K1 k1, K2 k2, size_t smem1, size_t smem2, int n_local, F launch) {
-    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    if (e != cudaSuccess) return e;
+  static int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 148;
+    }
+    return sms;
+  }
+  static bool want_split(int ctas) {
+    if (!kSplit) return false;
+    const char *e = getenv("CBFSSM_B200_TC_SPLIT");      // 0: never, 1: always (tests), unset: by launch size
+    if (e != nullptr && *e) return atoi(e) != 0;
+    return ctas <= sm_count();
+  }
+
+  // Launch `k1` (one particle tile per CTA), or `ks` (one tile, kSplitG threads per particle) when the launch is
+  // latency-bound, or, when only one one-tile CTA fits an SM and the two-tile CTA fits at all, `k2` (two tiles
+  // sharing P and the tables).  `launch(kernel, grid_x, threads, smem)` enqueues.
+  template <class K1, class K2, class KS, class F>
+  static cudaError_t pick(K1 k1, K2 k2, KS ks, size_t smem1, size_t smem2, size_t smems, int n_local, int nchain, F launch) {
     const int tiles = ceil_div(n_local, kTcThreads);
+    cudaError_t e;
+    if constexpr (kSplit) {
+      if (want_split(tiles * nchain) && smems <= kMaxDyn) {
+        e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems);
+        if (e != cudaSuccess) return e;
+        launch(ks, tiles, kSplitG * kTcThreads, smems);
+        return cudaGetLastError();
+      }
+    }
+    e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if (e != cudaSuccess) return e;
     if constexpr (kDual) {
       int nb = 0;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1, kTcThreads, smem1);
@@ -1096,6 +1200,7 @@ struct LaunchTc {
     launch(k1, tiles, kTcThreads, smem1);
     return cudaGetLastError();
   }
+  static constexpr int G = kSplit ? kSplitG : 1;
 
   static cudaError_t fw_reverse(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
                                 const float *y, const float *eps_f, float w_ll, float w_kl, Workspace ws,
@@ -1103,14 +1208,15 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, win, spart, nsc); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DX, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, true, 0, 2>::bytes(D.M);
+    const size_t s1 = TcCtx<DIN, DX, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, true, 0, 2>::bytes(D.M),
+                 ss = TcCtx<DIN, DX, true, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(fw_reverse_tc_kernel<DX, DU, DY, 100, 1>, fw_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
-                    D.n_local, launch);
+        return pick(fw_reverse_tc_kernel<DX, DU, DY, 100, 1>, fw_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+                    fw_reverse_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, 1, launch);
     }
-    return pick(fw_reverse_tc_kernel<DX, DU, DY, 0, 1>, fw_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
-                launch);
+    return pick(fw_reverse_tc_kernel<DX, DU, DY, 0, 1>, fw_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+                fw_reverse_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, 1, launch);
   }
   static cudaError_t bm_reverse(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
                                 const float *y, const float *eps_b, const float *z_b, float w_en, Workspace ws,
@@ -1119,14 +1225,15 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats, spart, nsc); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DH, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, true, 0, 2>::bytes(D.M);
+    const size_t s1 = TcCtx<DIN, DH, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, true, 0, 2>::bytes(D.M),
+                 ss = TcCtx<DIN, DH, true, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(bm_reverse_tc_kernel<DX, DU, DY, 100, 1>, bm_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
-                    D.n_local, launch);
+        return pick(bm_reverse_tc_kernel<DX, DU, DY, 100, 1>, bm_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+                    bm_reverse_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
     }
-    return pick(bm_reverse_tc_kernel<DX, DU, DY, 0, 1>, bm_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
-                launch);
+    return pick(bm_reverse_tc_kernel<DX, DU, DY, 0, 1>, bm_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+                bm_reverse_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
   }
 
   static cudaError_t bm_forward(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
@@ -1136,14 +1243,15 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DH, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, false, 0, 2>::bytes(D.M);
+    const size_t s1 = TcCtx<DIN, DH, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, false, 0, 2>::bytes(D.M),
+                 ss = TcCtx<DIN, DH, false, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(bm_forward_tc_kernel<DX, DU, DY, 100, 1>, bm_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
-                    D.n_local, launch);
+        return pick(bm_forward_tc_kernel<DX, DU, DY, 100, 1>, bm_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+                    bm_forward_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
     }
-    return pick(bm_forward_tc_kernel<DX, DU, DY, 0, 1>, bm_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
-                launch);
+    return pick(bm_forward_tc_kernel<DX, DU, DY, 0, 1>, bm_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+                bm_forward_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
   }
   static cudaError_t fw_forward(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
                                 const float *y, const float *eps_f, Workspace ws, float *part_out,
@@ -1151,14 +1259,15 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, ws, part_out); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DX, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, false, 0, 2>::bytes(D.M);
+    const size_t s1 = TcCtx<DIN, DX, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, false, 0, 2>::bytes(D.M),
+                 ss = TcCtx<DIN, DX, false, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(fw_forward_tc_kernel<DX, DU, DY, 100, 1>, fw_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>, s1, s2,
-                    D.n_local, launch);
+        return pick(fw_forward_tc_kernel<DX, DU, DY, 100, 1>, fw_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+                    fw_forward_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, 1, launch);
     }
-    return pick(fw_forward_tc_kernel<DX, DU, DY, 0, 1>, fw_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>, s1, s2, D.n_local,
-                launch);
+    return pick(fw_forward_tc_kernel<DX, DU, DY, 0, 1>, fw_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+                fw_forward_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, 1, launch);
   }
 };
 

@@ -180,6 +180,41 @@ def test_tensor_path_time_windows_match_oracle(shape, budget, monkeypatch):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("split", ["0", "1"], ids=["one_thread_per_particle", "four_threads_per_particle"])
+@pytest.mark.parametrize("case", [
+    (4, 1, 1, 100, 10, 2, 30, 10, 1.0, (10.0, 0.0), True, False),        # M = 100 compile-time instantiation
+    (4, 2, 2, 100, 16, 8, 40, 10, 1.0, (10.0, 0.3), True, True),
+    (4, 2, 2, 128, 20, 7, 12, 4, 1.0, (10.0, 0.3), True, True),          # runtime M, 8 chunks: 2 per group
+    (4, 1, 1, 24, 40, 2, 20, 4, 1.0, (10.0, 1.0), False, True),          # 2 chunks: groups 2, 3 own no rows
+    (3, 1, 1, 40, 37, 5, 13, 3, 3.0, (6.0, 1.0), True, True),            # 3 chunks, 2 ragged tiles
+], ids=lambda c: "dx%d_du%d_dy%d_M%d_S%d_B%d_T%d_R%d" % c[:8])
+def test_tensor_path_latency_variant_matches_oracle(case, split, monkeypatch):
+    """The tensor path has a latency variant (4 threads per particle, each a quarter of the M rows; chosen when a
+    launch has fewer CTAs than the GPU has SMs) besides the throughput variant (1 thread per particle).  Every parity
+    case in this file is small enough to get the former by default; this test forces each variant in turn, also
+    through the time-window machinery."""
+    monkeypatch.setenv("CBFSSM_B200_TC_SPLIT", split)
+    dx, du, dy, M, S, B, T, R, kap, lf, cond, strong = case
+    cfg, params, u, y, eps_b, z_b, eps_f = make_problem(dx, du, dy, M, S, B, T, R, kap, lf, seed=17, strong=strong)
+    res, gd = O.loss_and_grads(cfg, params, u, y, eps_b, z_b, eps_f, cond)
+    for budget in (None, "200000"):
+        if budget is None:
+            monkeypatch.delenv("CBFSSM_B200_TC_WINDOW_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("CBFSSM_B200_TC_WINDOW_BYTES", budget)
+        eng, out, yd = run_engine(cfg, params, u, y, eps_b, z_b, eps_f, cond, 8)
+        for k in ("loss", "loglik", "kl_x", "entropy"):
+            ref, got = float(getattr(res, k).detach()), float(out[k])
+            assert abs(got - ref) <= TOL * max(abs(ref), 1e-3), (k, got, ref, budget)
+        xf, yt = eng.export_states(yd)
+        assert rel_inf(xf.cpu().numpy(), res.x_final.detach().numpy()) < TOL
+        assert rel_inf(yt.cpu().numpy(), res.y_tilde.detach().numpy()) < TOL
+        grads = eng.get_grads()
+        bad = {k: rel_inf(grads[k], gd[k].numpy()) for k in O.PARAM_NAMES}
+        bad = {k: v for k, v in bad.items() if not v < TOL}
+        assert not bad, (bad, budget)
+
+
 def _cond_kzz(params, tag):
     """2-norm condition number of K_zz + 1e-8 I as the reference forms it (gp_tf.py:48-54)."""
     import torch
