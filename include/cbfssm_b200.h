@@ -9,9 +9,16 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the parameter is named *_host;
  *   - the caller owns every buffer, including the workspace; the library never
- *     allocates or frees device memory and keeps no global state;
+ *     allocates or frees device memory.  Process-wide state it does keep: (1) the
+ *     register-resident kernels (compiled-in small M) read their packed GP operands from a
+ *     per-instantiation __constant__ image that every call refreshes on its stream, so two
+ *     calls for the same (dims, M) must not run concurrently on different streams of one
+ *     process; (2) the float64 path holds one cuBLAS handle per host thread; (3) the
+ *     thread-local measurement aids below (off by default);
  *   - all work is enqueued on the cudaStream_t passed in (as void*), no internal
- *     synchronisation; re-entrant; one host thread per GPU;
+ *     synchronisation (except cbf_timing_read and cbf_measure_fp32_peak, which say so); one
+ *     host thread per GPU; calls on one stream are re-entrant in the sense that they keep
+ *     nothing between calls except the caller's workspace;
  *   - return value: 0 ok, negative = CBF_ERR_* below, positive = cudaError_t;
  *     cbf_last_error_string() gives a thread-local description;
  *   - pointers must be 16-byte aligned.
