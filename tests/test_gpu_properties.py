@@ -337,3 +337,28 @@ def test_register_path_saved_evaluations_equal_recomputation(monkeypatch):
         outs.append((eng._gflat.clone(), eng.terms.clone(), int(eng._ws.numel())))
     assert outs[1][2] > outs[0][2]                       # the saved evaluations live in the workspace
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("M,B,T,flags", [(20, 4544, 300, 4), (100, 1515, 100, 8)], ids=["register_m20_bench_shape", "tensor_m100_bench_shape"])
+def test_bench_scale_float32_accumulation_against_the_float64_path(M, B, T, flags):
+    """Accuracy at the length the bench runs, not only at the <= 1 600 particles the oracle can afford: the float32
+    paths' ELBO terms and all 12 gradients at the full bench shape (227 200 particles x 300 steps at M = 20,
+    75 750 x 100 at M = 100: up to 7e7 particle-steps accumulated per tensor entry in float32 per warp / per CTA,
+    float64 across them) against the float64 batched path on the same inputs, which accumulates everything in
+    double and is itself checked against the oracle at 2e-5."""
+    eng = _engine(M=M, S=50, R=50, lf=(20.0, 0.1))
+    u, y, eb, zb, ef = _inputs(eng, B, T, seed=6)
+    res = {}
+    for name, fl in (("f32", flags), ("f64", 128)):
+        eng.flags = fl
+        out = eng.forward(u, y, eb, zb, ef, True)
+        eng.backward()
+        torch.cuda.synchronize()
+        res[name] = ({k: float(v) for k, v in out.items()}, {k: v.copy() for k, v in eng.get_grads().items()})
+    for k in ("loss", "loglik", "kl_x", "entropy"):
+        a, b = res["f32"][0][k], res["f64"][0][k]
+        assert abs(a - b) <= 2e-5 * abs(b), (k, a, b)
+    worst = {k: rel_inf(res["f32"][1][k], res["f64"][1][k]) for k in O.PARAM_NAMES}
+    print("bench-scale float32 vs float64:", {k: "%.1e" % v for k, v in worst.items()})
+    bad = {k: v for k, v in worst.items() if not v < 1e-4}
+    assert not bad, bad
