@@ -1,3 +1,5 @@
 from .outputs import Outputs
 
-__all__ = ["Outputs"]
+from .output_summary import OutputSummary
+
+__all__ = ["Outputs", "OutputSummary"]

@@ -234,3 +234,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["vs_baseline"] is None and line["gpu_launches"] == 0
+
+
+def test_output_summary_writes_the_reference_layout(tmp_path):
+    """summary.txt of repeated runs (cbfssm/outputs/output_summary.py:19-31): runs, mean, population std."""
+    from cbf_ssm_b200.outputs import OutputSummary
+
+    class FakeOutputs:
+        def __init__(self, v):
+            self.v = v
+
+        def get_last_rmse(self):
+            return self.v
+    summ = OutputSummary(str(tmp_path / "s"), copy_main=False)
+    for v in (0.5, 0.7, 0.9):
+        summ.add_outputs(FakeOutputs(v))
+    path = summ.write_summary()
+    text = open(path).read().split("\n")
+    assert text[:4] == ["RMSE", "====", "", "Runs:"] and text[4:7] == ["  0.500000", "  0.700000", "  0.900000"]
+    assert text[7] == "Mean: 0.700000" and text[8] == "Std:  %f" % np.std([0.5, 0.7, 0.9])
+    empty = OutputSummary(str(tmp_path / "e"), copy_main=False)
+    empty.add_outputs(FakeOutputs(None))
+    assert empty.write_summary() is None and not os.path.exists(tmp_path / "e" / "summary.txt")
