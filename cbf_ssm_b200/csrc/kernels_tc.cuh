@@ -1083,13 +1083,20 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     }
   };
   float hnext[DH];   // fetched one step ahead (it heads the step's dependency chain)
+  float ynext[DH];   // adjoint of y2[t], likewise: its load sat directly in front of its use (4 % of the samples)
+  auto load_ybar = [&](int t, float(&yv)[DH]) {
+    const float *Yq = ws.Yb + ((size_t)t * DH) * np + nr;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) yv[j] = Yq[j * np];
+  };
   load_hidden(ch.t_lo, hnext);
+  load_ybar(ch.t_lo, ynext);
 #pragma unroll 1
   for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
-    float hid[DH], xin[DIN], xt[Ctx::DINP], fm[DH], fv[DH], amax, kscale;
+    float hid[DH], ybar[DH], xin[DIN], xt[Ctx::DINP], fm[DH], fv[DH], amax, kscale;
 #pragma unroll
-    for (int j = 0; j < DH; ++j) hid[j] = hnext[j];
-    if (t < ch.t_hi) load_hidden(t + 1, hnext);
+    for (int j = 0; j < DH; ++j) { hid[j] = hnext[j]; ybar[j] = ynext[j]; }
+    if (t < ch.t_hi) { load_hidden(t + 1, hnext); load_ybar(t + 1, ynext); }
 #pragma unroll
     for (int j = 0; j < DH; ++j) xin[j] = hid[j];
 #pragma unroll
@@ -1101,13 +1108,12 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale);
     const bool write = writer_run(t, D.R) == ch.run;
     float ob[DH], fvb[DH];
-    const float *Yp = ws.Yb + ((size_t)t * DH) * np + nr;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
       const float f = fv[j] + vx[j];
       float ov = hb[j], fb = 0.f;
       if (write) {
-        ov += Yp[j * np];
+        ov += ybar[j];
         fb = w_en * 0.5f / f;
       }
       fb += ov * e * 0.5f * rsqrtf(f);

@@ -27,6 +27,17 @@ from .base_model import BaseModel, Fetch, OutOfRangeError
 _PRED = ("pred_mean", "pred_var", "internal_mean", "internal_var", "mse", "sde", "x_final", "y_final", "y_tilde")
 
 
+def precision_flags(cfg):
+    """``config['gpu_precision']`` (not a reference key): 'float32' (default) runs the float32 rollout kernels the
+    north-star asks for (1e-4 against the float64 reference while cond(K_zz) <~ 1e3); 'float64' selects the float64
+    batched path (CBF_FLAG_FP64) -- the reference's own default dtype (base_model.py:8), ~20x slower at M = 100, for
+    inducing sets float32 cannot resolve.  M > 128 always runs in float64."""
+    prec = str(cfg.get("gpu_precision", "float32"))
+    if prec not in ("float32", "float64"):
+        raise ValueError("config['gpu_precision'] must be 'float32' or 'float64'")
+    return 128 if prec == "float64" else 0
+
+
 class Saver:
     """tf.train.Saver look-alike (cbfssm.py:276; trainer.py:31,59,63): like the reference's, it persists
     *every* variable of the model -- whatever ``model.state_dict()`` returns (the 12 tensors and their Adam
@@ -67,6 +78,7 @@ class CBFSSM(BaseModel):
         self.world = torch.distributed.get_world_size(self._group) if self._group is not None else 1
         self.rank = torch.distributed.get_rank(self._group) if self._group is not None else 0
         self.engine = ElboEngine(self.dims, device=self._device, group=self._group if self.world > 1 else None)
+        self.engine.flags = precision_flags(cfg)
         for name in ("loss", "train", "init", "entropy", "kl_x") + _PRED:
             setattr(self, name, self._handle(name))
         # cbfssm.py:56-67

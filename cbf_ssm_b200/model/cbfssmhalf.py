@@ -15,7 +15,7 @@ import torch
 
 from ..engine import ElboEngine, ModelDims, init_param_arrays
 from .base_model import BaseModel
-from .cbfssm import CBFSSM, Saver
+from .cbfssm import CBFSSM, Saver, precision_flags
 
 GRU_UNITS = 16
 
@@ -46,6 +46,7 @@ class CBFSSMHALF(CBFSSM):
         if self.world > 1:
             raise NotImplementedError("CBFSSMHALF: single GPU (replicas only) in this round")
         self.engine = ElboEngine(self.dims, device=self._device, group=None)
+        self.engine.flags = precision_flags(cfg)
         for name in ("loss", "train", "init", "entropy", "kl_x", "pred_mean", "pred_var", "internal_mean",
                      "internal_var", "mse", "sde", "x_final", "y_final", "y_tilde"):
             setattr(self, name, self._handle(name))

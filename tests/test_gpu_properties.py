@@ -362,3 +362,35 @@ def test_bench_scale_float32_accumulation_against_the_float64_path(M, B, T, flag
     print("bench-scale float32 vs float64:", {k: "%.1e" % v for k, v in worst.items()})
     bad = {k: v for k, v in worst.items() if not v < 1e-4}
     assert not bad, bad
+
+
+def test_model_level_float64_precision_switch():
+    """config['gpu_precision'] = 'float64' runs the model on the float64 batched path: same loss as float32 to
+    float32 accuracy on a well-conditioned problem, and training still works through the reference-shaped API."""
+    from cbf_ssm_b200.datasets import SpringNonlinearSynthetic
+    from cbf_ssm_b200.model import CBFSSM
+
+    class SmallSpring(SpringNonlinearSynthetic):
+        exp_len = 300
+    ds = SmallSpring(20, 10, seed=2)
+    base = {'ds': SmallSpring, 'batch_size': 4, 'shuffle': 1, 'dim_x': 4, 'ind_pnt_num': 20, 'samples': 8,
+            'learning_rate': 0.01, 'loss_factors': np.asarray([10., 0.2]), 'k_factor': 1., 'recog_len': 6,
+            'zeta_pos': 2., 'zeta_mean': 0.1 ** 2, 'zeta_var': 0.01 ** 2, 'var_x': np.asarray([0.1 ** 2] * 4),
+            'var_y': np.asarray([1. ** 2] * 4), 'gp_var': 0.1 ** 2, 'gp_len': 1.}
+    u, y = ds.train_in_batch[:4], ds.train_out_batch[:4]
+    T = u.shape[1]
+    g = np.random.default_rng(1)
+    draws = (g.standard_normal((2, T, 4, 8)), g.standard_normal((2, T, 4, 8)), g.standard_normal((T - 1, 4, 8)))
+    losses = {}
+    for prec in ("float32", "float64"):
+        m = CBFSSM(dict(base, gpu_precision=prec), seed=3)
+        assert m.engine.flags == (128 if prec == "float64" else 0)
+        m.inject_draws(*draws)
+        l0 = float(m.evaluate_batch(u, y, ["train", "loss"], True)[1])
+        m.inject_draws(*draws)
+        l1 = float(m.evaluate_batch(u, y, ["train", "loss"], True)[1])
+        assert l1 < l0                                   # one Adam step on the same minibatch and draws
+        losses[prec] = (l0, l1)
+    assert losses["float32"][0] == pytest.approx(losses["float64"][0], rel=1e-5)
+    with pytest.raises(ValueError):
+        CBFSSM(dict(base, gpu_precision="float16"), seed=3)

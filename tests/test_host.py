@@ -224,9 +224,16 @@ def test_bench_reference_arm_prints_the_contract_line():
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=600, check=True).stdout
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--workload", "spring_template_b32"], capture_output=True, text=True,
+                         timeout=600, check=True).stdout
     line = json.loads(out.strip().splitlines()[-1])
+    # the CPU arm prints the same workload description the GPU arm prints (bench.config_dict), honours --steps /
+    # --warmup as given, and adds the reference's own thread setting (trainer.py:24) and its rate-vs-batch sweep
+    import bench
+    w = bench.WORKLOADS["spring_template_b32"]
+    assert line["config"] == bench.config_dict(w, w["batch"], 1, "weak") and line["steps"] == 2 and line["warmup"] == 1
+    assert line["cpu_baseline"]["five_threads"]["threads"] == min(5, os.cpu_count()) and line["cpu_baseline"]["rate_vs_sample_batch"]
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert key in line, key
