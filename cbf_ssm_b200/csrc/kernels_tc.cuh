@@ -425,17 +425,19 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   }
   // packed FP32 (FADD2 / FFMA2 / FMUL2): pairs of input dims for delta, pairs of output dims for the sums
   constexpr int J2 = (DIN + 1) / 2, D2 = (DOUT + 1) / 2;
-  unsigned long long x2[J2], fm2[D2], fv2[D2];
+  // Every sum over the inducing rows runs as two interleaved chains (even / odd rows): with two warps per
+  // scheduler a single 16-long dependent FMA chain per chunk leaves the issue slot idle for its latency.
+  unsigned long long x2[J2], fm2[D2], fv2[D2], fm2b[D2], fv2b[D2];
 #pragma unroll
   for (int j = 0; j < J2; ++j) x2[j] = pack2(xt[2 * j], xt[2 * j + 1]);   // xt is zero-padded to DINP
 #pragma unroll
-  for (int d = 0; d < D2; ++d) { fm2[d] = 0ull; fv2[d] = 0ull; }
+  for (int d = 0; d < D2; ++d) { fm2[d] = 0ull; fv2[d] = 0ull; fm2b[d] = 0ull; fv2b[d] = 0ull; }
   // ---- kernel vector -> fp16 split operands ----
   // fp16 has a narrow exponent range and k' = exp(-d^2/2) can be 1e-12 for every inducing point (e.g.
   // 21 input dims), so each particle's vector is normalised by its own maximum: pass 1 parks the squared
   // distances (float32) in the thread's own K1/K2 slots and finds their minimum, pass 2 forms
   // k'' = exp(-(d^2 - d^2_min)/2) in (0,1] (max exactly 1), splits and overwrites.  k' = kscale * k''.
-  float d2min = 3.0e38f;
+  float d2min = 3.0e38f, d2minb = 3.0e38f;
 #pragma unroll 1
   for (int cc = g0; cc < MP / 16; cc += NG)
 #pragma unroll
@@ -454,13 +456,14 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
         acc = fma2(dl, dl, acc);
       }
       const float d2 = hsum2(acc);
-      d2min = fminf(d2min, d2);
+      if (e & 1) d2minb = fminf(d2minb, d2); else d2min = fminf(d2min, d2);
       dv[e] = d2;
     }
     const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
     *reinterpret_cast<float4 *>(c.K1 + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
     *reinterpret_cast<float4 *>(c.K2 + off) = make_float4(dv[4], dv[5], dv[6], dv[7]);
   }
+  d2min = fminf(d2min, d2minb);
   if (NG > 1) {   // the particle's minimum over all groups
     *c.xslot(g0, 0) = d2min;
     __syncthreads();
@@ -485,7 +488,10 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       ld_row<DOUTP>(c.al + m * DOUTP, al);
       const unsigned long long kk = pack2(kp, kp);
 #pragma unroll
-      for (int d = 0; d < D2; ++d) fm2[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2[d]);
+      for (int d = 0; d < D2; ++d) {
+        if (e & 1) fm2b[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2b[d]);
+        else fm2[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2[d]);
+      }
       kv[e] = kp;
     }
     tc_write_row8(c.K1, c.K2, t, ch, kv);
@@ -499,7 +505,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   // ---- D1 = K P' on the tensor core ----
   tc_contract(c, c.K1, c.K2, c.tmem);
   // ---- accumulator row back: q' = k'.a', v'_d = sum a'^2 S ----
-  float q = 0.f;
+  float q = 0.f, qb = 0.f, amaxb = 0.f;
   amax = 0.f;
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
   uint32_t ra[16];
@@ -515,18 +521,29 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int m = cc * 16 + e;
-      q = fmaf(kp[e], a[e], q);
-      amax = fmaxf(amax, fabsf(a[e]));
       const float a2 = a[e] * a[e];
       float S[DOUTP];
       ld_row<DOUTP>(c.Sm + m * DOUTP, S);
       const unsigned long long aa = pack2(a2, a2);
+      if (e & 1) {
+        qb = fmaf(kp[e], a[e], qb);
+        amaxb = fmaxf(amaxb, fabsf(a[e]));
 #pragma unroll
-      for (int d = 0; d < D2; ++d) fv2[d] = fma2(pack2(S[2 * d], S[2 * d + 1]), aa, fv2[d]);
+        for (int d = 0; d < D2; ++d) fv2b[d] = fma2(pack2(S[2 * d], S[2 * d + 1]), aa, fv2b[d]);
+      } else {
+        q = fmaf(kp[e], a[e], q);
+        amax = fmaxf(amax, fabsf(a[e]));
+#pragma unroll
+        for (int d = 0; d < D2; ++d) fv2[d] = fma2(pack2(S[2 * d], S[2 * d + 1]), aa, fv2[d]);
+      }
     }
   }
+  q += qb;
+  amax = fmaxf(amax, amaxb);
 #pragma unroll
   for (int d = 0; d < D2; ++d) {
+    fm2[d] = add2(fm2[d], fm2b[d]);
+    fv2[d] = add2(fv2[d], fv2b[d]);
     float m0, m1, v0, v1;
     unpack2(fm2[d], m0, m1);
     unpack2(fv2[d], v0, v1);
@@ -637,11 +654,12 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   const float pbs = ps * ascale * binv;         // (P b)_m = pbs * (P' b'')_m
   const float bs = ascale * binv;               // b_m = bs * b''_m
   constexpr int J2 = (DIN + 1) / 2, N2 = (NEED + 1) / 2;
-  unsigned long long x2[J2], xs2[N2], L2[J2];   // packed over input-dim pairs (2j, 2j+1)
+  unsigned long long x2[J2], xs2[N2], L2[J2], xs2b[N2], L2b[J2];   // packed over input-dim pairs (2j, 2j+1); two chains (even / odd rows)
+  float swb = 0.f;
 #pragma unroll
-  for (int j = 0; j < J2; ++j) { x2[j] = pack2(xt[2 * j], xt[2 * j + 1]); L2[j] = 0ull; }
+  for (int j = 0; j < J2; ++j) { x2[j] = pack2(xt[2 * j], xt[2 * j + 1]); L2[j] = 0ull; L2b[j] = 0ull; }
 #pragma unroll
-  for (int j = 0; j < N2; ++j) xs2[j] = 0ull;
+  for (int j = 0; j < N2; ++j) { xs2[j] = 0ull; xs2b[j] = 0ull; }
 #pragma unroll(MC ? kTcChunkUnroll : 1)
   for (int cc = g0; cc < MP / 16; cc += NG) {
     float pb[16], a[16], kp[16], bb[16];
@@ -675,7 +693,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gm[d], kb);
       const float k = sig2 * kp[e];
       const float w = kb * k;
-      sw += w;
+      if (e & 1) swb += w; else sw += w;
       float z[DINP];
       ld_row<DINP>(c.Zt + m * DINP, z);
       const unsigned long long ww = pack2(w, w);
@@ -683,8 +701,13 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       for (int j = 0; j < J2; ++j) {
         const unsigned long long dl = add2(x2[j], pack2(z[2 * j], z[2 * j + 1]));
         const unsigned long long wd = mul2(dl, ww);
-        if (j < N2) xs2[j < N2 ? j : 0] = add2(xs2[j < N2 ? j : 0], wd);
-        L2[j] = fma2(wd, dl, L2[j]);
+        if (e & 1) {
+          if (j < N2) xs2b[j < N2 ? j : 0] = add2(xs2b[j < N2 ? j : 0], wd);
+          L2b[j] = fma2(wd, dl, L2b[j]);
+        } else {
+          if (j < N2) xs2[j < N2 ? j : 0] = add2(xs2[j < N2 ? j : 0], wd);
+          L2[j] = fma2(wd, dl, L2[j]);
+        }
       }
       wv[e] = w;
       abv[e] = 2.f * bs * bb[e] - Gs * k;
@@ -701,8 +724,12 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       if (2 * cc + 1 < o.MB) o.put8(o.bAb + 2 * cc + 1, hi);
     }
   }
+  sw += swb;
+#pragma unroll
+  for (int j = 0; j < N2; ++j) xs2[j] = add2(xs2[j], xs2b[j]);
 #pragma unroll
   for (int j = 0; j < J2; ++j) {
+    L2[j] = add2(L2[j], L2b[j]);
     float l0, l1;
     unpack2(L2[j], l0, l1);
     Lacc[2 * j] += l0;
