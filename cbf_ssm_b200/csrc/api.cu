@@ -125,6 +125,8 @@ struct Plan {
   size_t off_x0b;
   size_t off_kaf, off_kab;       // register path: saved evaluations (0 = not saved)
   bool save_eval;
+  size_t off_fvf, off_fvb;       // tensor path: saved (fmean, fvar, amax) per evaluation
+  bool save_fv;
   bool f64;                      // float64 batched path (f64_path.cu): M > 128, dims without an instantiation, CBF_FLAG_FP64
   size_t off_f64;
   // tensor-core path (16 <= M <= 128, enough particles)
@@ -265,6 +267,7 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
   }
   // ---- tensor-core path ----
   p.tc_fwd = p.tc_rev = false;
+  p.save_fv = false; p.off_fvf = p.off_fvb = 0;
   if (p.ops && p.ops->fw_forward_tc != nullptr && s->M >= kMinTensorM && s->M <= 128 &&
       !(s->flags & (CBF_FLAG_FORCE_COOPERATIVE | CBF_FLAG_NO_TENSOR_CORES)) &&
       ((s->flags & CBF_FLAG_FORCE_TENSOR_CORES) || s->n_local >= kMinParticlesTensorPath)) {
@@ -345,6 +348,15 @@ static int make_plan(const cbf_shape *s, Plan &p, bool need_ops) {
       p.off_rdb = o; o = align_up(o + sizeof(double) * (size_t)s->M * p.ctot_b, 256);
       p.off_carry_f = o; o = align_up(o + sizeof(float) * p.dx * np, 256);
       p.off_carry_b = o; o = align_up(o + sizeof(float) * (p.chains.size() + 1) * p.dh * np, 256);
+      // moments of every evaluation, left by the forward kernels so that the reverse kernels recompute only the
+      // kernel vector and a = P k (36 / 20 B per evaluation at D = 4)
+      const size_t fvf = sizeof(float) * (size_t)(2 * p.dx + 1) * np * (size_t)(s->T - 1);
+      const size_t fvb = p.half ? 0 : sizeof(float) * (size_t)(2 * p.dh + 1) * np * (size_t)(2 * s->T);
+      if (!(s->flags & CBF_FLAG_PREDICT_ONLY) && fvf + fvb <= saved_eval_budget()) {
+        p.save_fv = true;
+        p.off_fvf = o; o = align_up(o + fvf, 256);
+        p.off_fvb = o; o = align_up(o + fvb + 16, 256);
+      }
     }
   }
   if (p.f64) {
@@ -413,6 +425,8 @@ static Workspace bind_workspace(const Plan &p, void *base) {
   w.cpack = reinterpret_cast<float *>(b + p.off_cpack);
   w.carry_f = p.tc_rev ? reinterpret_cast<float *>(b + p.off_carry_f) : nullptr;
   w.carry_b = p.tc_rev ? reinterpret_cast<float *>(b + p.off_carry_b) : nullptr;
+  w.FVf = p.save_fv ? reinterpret_cast<float *>(b + p.off_fvf) : nullptr;
+  w.FVb = (p.save_fv && !p.half) ? reinterpret_cast<float *>(b + p.off_fvb) : nullptr;
   w.KAf = p.save_eval ? reinterpret_cast<float4 *>(b + p.off_kaf) : nullptr;
   w.KAb = (p.save_eval && !p.half) ? reinterpret_cast<float4 *>(b + p.off_kab) : nullptr;
   w.x0 = nullptr;

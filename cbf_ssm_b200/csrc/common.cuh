@@ -83,6 +83,8 @@ struct Workspace {
   float *carry_f;  // [dx][npad]            state adjoint between time windows (tensor path)
   float *carry_b;  // [chains][dh][npad]    message adjoint between chain pieces (tensor path)
   float *cpack;    // [2][2048] packed constant-bank images of the two GPs (register path)
+  float *FVf;      // tensor path, optional: saved (fmean[dx], fvar[dx], amax) of every forward-rollout GP evaluation,
+  float *FVb;      //   ... of every backward-message evaluation (slot = run * T + t): plane v of slot e at ((e * NV + v) * npad + n)
   float4 *KAf;     // register path, optional: saved (k, a, fmean, fvar) of every forward-rollout GP evaluation
   float4 *KAb;     //                          ... of every backward-message evaluation, slot = run * T + t
   const float *x0; // CBFSSMHALF: x_0 per sequence [B][dx] (output of the recognition model)

@@ -409,10 +409,12 @@ struct TcOut {
 // kscale: the particle's normalisation, k' = kscale * k''.
 // With NG groups (Ctx::NG > 1) a thread handles the 16-row chunks cc = grp, grp + NG, ...; every result
 // (fm, fv, amax, kscale) is the same in all NG threads of a particle.
+// light (reverse kernels, when the forward kernels saved fm / fv / amax): only the kernel vector, its operand rows
+// and D1 = K P' are produced; fm, fv, amax are left as the caller set them.
 template <class Ctx, int DIN, int DOUT>
 __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], float (&xt)[(DIN + 3) / 4 * 4],
                                               float (&fm)[DOUT], float (&fv)[DOUT], const TcOut *kout,
-                                              float &amax, float &kscale) {
+                                              float &amax, float &kscale, const bool light = false) {
   constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
   constexpr int MC = Ctx::MC, NG = Ctx::NG;
   const int t = c.lane_id(), g0 = c.grp(), M = MC ? MC : c.M, MP = MC ? (MC + 15) / 16 * 16 : c.MP;
@@ -484,13 +486,15 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
     for (int e = 0; e < 8; ++e) {
       const int m = ch * 8 + e;
       const float kp = fast_exp2(kNegHalfLog2e * (dv[e] - d2min));
-      float al[DOUTP];
-      ld_row<DOUTP>(c.al + m * DOUTP, al);
-      const unsigned long long kk = pack2(kp, kp);
+      if (!light) {
+        float al[DOUTP];
+        ld_row<DOUTP>(c.al + m * DOUTP, al);
+        const unsigned long long kk = pack2(kp, kp);
 #pragma unroll
-      for (int d = 0; d < D2; ++d) {
-        if (e & 1) fm2b[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2b[d]);
-        else fm2[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2[d]);
+        for (int d = 0; d < D2; ++d) {
+          if (e & 1) fm2b[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2b[d]);
+          else fm2[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2[d]);
+        }
       }
       kv[e] = kp;
     }
@@ -504,6 +508,10 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   }
   // ---- D1 = K P' on the tensor core ----
   tc_contract(c, c.K1, c.K2, c.tmem);
+  if (light) {     // uniform over the CTA: the moments come from the forward pass
+    tc_fence_before();
+    return;
+  }
   // ---- accumulator row back: q' = k'.a', v'_d = sum a'^2 S ----
   float q = 0.f, qb = 0.f, amaxb = 0.f;
   amax = 0.f;
@@ -832,6 +840,12 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
     float xt[Ctx::DINP], amax, kscale;
     gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, nullptr, amax, kscale);
+    if (ws.FVb != nullptr && live && c.grp() == 0) {
+      float *Fp = ws.FVb + (((size_t)ch.run * D.T + t) * (2 * DH + 1)) * np + nl;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) { Fp[(size_t)j * np] = fm[j]; Fp[(size_t)(DH + j) * np] = fv[j]; }
+      Fp[(size_t)(2 * DH) * np] = amax;
+    }
     const bool write = writer_run(t, D.R) == ch.run;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
@@ -912,6 +926,12 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     const float e = eps_f[(size_t)t * D.n_local + nr];
     float xt[Ctx::DINP], amax, kscale;
     gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, nullptr, amax, kscale);
+    if (ws.FVf != nullptr && live && c.grp() == 0) {
+      float *Fp = ws.FVf + ((size_t)t * (2 * DX + 1)) * np + nl;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) { Fp[(size_t)j * np] = fm[j]; Fp[(size_t)(DX + j) * np] = fv[j]; }
+      Fp[(size_t)(2 * DX) * np] = amax;
+    }
     const bool do_cond = D.condition || (t < D.R - 1);
     fw_step<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, xn, kl);
 #pragma unroll
@@ -988,6 +1008,14 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
 #pragma unroll
     for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
   }
+  const bool saved = ws.FVf != nullptr;      // (fmean, fvar, amax) of every step left by fw_forward_tc
+  float fnext[2 * DX + 1];
+  auto load_saved = [&](int t) {
+    const float *Fp = ws.FVf + ((size_t)t * (2 * DX + 1)) * np + nr;
+#pragma unroll
+    for (int j = 0; j < 2 * DX + 1; ++j) fnext[j] = Fp[(size_t)j * np];
+  };
+  if (saved) load_saved(win.t_hi);
 #pragma unroll 1
   for (int t = win.t_hi; t >= win.t_lo; --t) {
     float x[DX], xin[DIN], xt[Ctx::DINP], fm[DX], fv[DX], yt[DX], amax, kscale;
@@ -1009,7 +1037,13 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     }
     const float e = eps_f[(size_t)t * D.n_local + nr];
     const TcOut o = tc_out_at(mats, (size_t)(t - win.t_lo) * D.n_local + nr);
-    gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale);
+    if (saved) {
+#pragma unroll
+      for (int j = 0; j < DX; ++j) { fm[j] = fnext[j]; fv[j] = fnext[DX + j]; }
+      amax = fnext[2 * DX];
+      if (t > win.t_lo) load_saved(t - 1);
+    }
+    gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale, saved);
     const bool do_cond = D.condition || (t < D.R - 1);
     float fmb[DX], fvb[DX], ytb[DX];
     fw_step_adjoint<DX>(x, fm, fv, yt, e, vx, vy, D.kap, do_cond, D.ncond, w_kl, xb, fmb, fvb, ytb, vxacc, vyacc,
@@ -1116,8 +1150,16 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
 #pragma unroll
     for (int j = 0; j < DH; ++j) yv[j] = Yq[j * np];
   };
+  const bool saved = ws.FVb != nullptr;      // (fmean, fvar, amax) of every step left by bm_forward_tc
+  float fnext[2 * DH + 1];
+  auto load_saved = [&](int t) {
+    const float *Fp = ws.FVb + (((size_t)ch.run * D.T + t) * (2 * DH + 1)) * np + nr;
+#pragma unroll
+    for (int j = 0; j < 2 * DH + 1; ++j) fnext[j] = Fp[(size_t)j * np];
+  };
   load_hidden(ch.t_lo, hnext);
   load_ybar(ch.t_lo, ynext);
+  if (saved) load_saved(ch.t_lo);
 #pragma unroll 1
   for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
     float hid[DH], ybar[DH], xin[DIN], xt[Ctx::DINP], fm[DH], fv[DH], amax, kscale;
@@ -1132,7 +1174,13 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     for (int j = 0; j < DY; ++j) xin[DH + DU + j] = yb[t * DY + j];
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
     const TcOut o = tc_out_at(mats, ((size_t)ch.col0 + (t - ch.t_lo)) * D.n_local + nr);
-    gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale);
+    if (saved) {
+#pragma unroll
+      for (int j = 0; j < DH; ++j) { fm[j] = fnext[j]; fv[j] = fnext[DH + j]; }
+      amax = fnext[2 * DH];
+      if (t < ch.t_hi) load_saved(t + 1);
+    }
+    gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale, saved);
     const bool write = writer_run(t, D.R) == ch.run;
     float ob[DH], fvb[DH];
 #pragma unroll

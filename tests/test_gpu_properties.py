@@ -318,17 +318,19 @@ def test_predict_only_skips_dead_message_work_and_changes_nothing(M):
     eng.backward()
 
 
-def test_register_path_saved_evaluations_equal_recomputation(monkeypatch):
-    """The register path keeps (k, a, fmean, fvar) of every GP evaluation for the reverse pass when the extra
-    workspace fits its budget, and recomputes them otherwise: both give bit-identical gradients."""
+@pytest.mark.parametrize("M,flags", [(20, 4), (100, 8)], ids=["register_m20", "tensor_m100"])
+def test_saved_evaluations_equal_recomputation(M, flags, monkeypatch):
+    """The register path keeps (k, a, fmean, fvar) of every GP evaluation for the reverse pass, the tensor path
+    (fmean, fvar, amax), when the extra workspace fits its budget; otherwise the reverse kernels recompute them:
+    both give bit-identical gradients."""
     outs = []
     for budget in ("0", None):
         if budget is None:
             monkeypatch.delenv("CBFSSM_B200_SAVE_EVAL_BYTES", raising=False)
         else:
             monkeypatch.setenv("CBFSSM_B200_SAVE_EVAL_BYTES", budget)
-        eng = _engine()
-        eng.flags = 4
+        eng = _engine(M=M, R=20, lf=(20.0, 0.3))
+        eng.flags = flags
         B, T = 7, 120
         u, y, eb, zb, ef = _inputs(eng, B, T, seed=2)
         eng.forward(u, y, eb, zb, ef, True)
