@@ -48,7 +48,14 @@ class Trainer:
         model = self.model
         model.load_ds(sess, data_in, data_out)
         results = model.run(sess, fetches, {model.condition: True})
-        return float(np.mean(results[-1]))          # loss is the last fetch
+        losses = np.asarray(results[-1], dtype=np.float64)          # loss is the last fetch
+        if not np.all(np.isfinite(losses)):
+            # The float32 kernels clamp the GP variance at its exact lower bound, so this is not the usual
+            # cancellation NaN; a non-finite loss means the parameters themselves have left the representable range
+            # (or cond(K_zz) is far beyond float32: try config['gpu_precision'] = 'float64').
+            raise FloatingPointError("non-finite ELBO in minibatch %d of this pass; the update was applied -- restore "
+                                     "the last checkpoint" % int(np.argmin(np.isfinite(losses))))
+        return float(np.mean(losses))
 
     def _particle_steps(self, windows):
         n_seq, seq_len = windows.shape[0], windows.shape[1]

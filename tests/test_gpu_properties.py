@@ -396,3 +396,32 @@ def test_model_level_float64_precision_switch():
     assert losses["float32"][0] == pytest.approx(losses["float64"][0], rel=1e-5)
     with pytest.raises(ValueError):
         CBFSSM(dict(base, gpu_precision="float16"), seed=3)
+
+
+def test_reference_checkpoint_export_import_round_trip(tmp_path):
+    """A model written as a TensorFlow-V2 checkpoint under the reference graph's variable names and read back into a
+    differently initialised model: parameters, Adam slots and step count identical (format: training/tf_checkpoint.py)."""
+    from cbf_ssm_b200.datasets import SpringNonlinearSynthetic
+    from cbf_ssm_b200.model import CBFSSM
+    from cbf_ssm_b200.training import export_reference_checkpoint, import_reference_checkpoint, read_tf_checkpoint
+
+    class SmallSpring(SpringNonlinearSynthetic):
+        exp_len = 300
+    ds = SmallSpring(20, 10, seed=2)
+    cfg = {'ds': SmallSpring, 'batch_size': 4, 'shuffle': 1, 'dim_x': 4, 'ind_pnt_num': 20, 'samples': 8,
+           'learning_rate': 0.01, 'loss_factors': np.asarray([10., 0.2]), 'k_factor': 1., 'recog_len': 6,
+           'zeta_pos': 2., 'zeta_mean': 0.1 ** 2, 'zeta_var': 0.01 ** 2, 'var_x': np.asarray([0.1 ** 2] * 4),
+           'var_y': np.asarray([1. ** 2] * 4), 'gp_var': 0.1 ** 2, 'gp_len': 1.}
+    a = CBFSSM(cfg, seed=3)
+    for _ in range(3):
+        a.evaluate_batch(ds.train_in_batch[:4], ds.train_out_batch[:4], ["train", "loss"], True)
+    prefix = str(tmp_path / "best.ckpt")
+    export_reference_checkpoint(a, prefix)
+    ck = read_tf_checkpoint(prefix)
+    assert ck["Variable"].shape == (20, 5) and ck["kern/Variable"].shape == (1,) and ck["Variable_7"].shape == (4,)
+    assert "Variable_3/Adam_1" in ck and float(ck["beta1_power"]) == pytest.approx(0.9 ** 4)
+    b = CBFSSM(cfg, seed=99)
+    loaded = import_reference_checkpoint(b, prefix)
+    assert len(loaded) == 12 * 3 + 1
+    assert torch.equal(a.engine.theta, b.engine.theta) and torch.equal(a.engine.adam_m, b.engine.adam_m)
+    assert torch.equal(a.engine.adam_v, b.engine.adam_v) and b.engine.adam_t == a.engine.adam_t == 3

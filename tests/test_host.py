@@ -263,3 +263,47 @@ def test_output_summary_writes_the_reference_layout(tmp_path):
     empty = OutputSummary(str(tmp_path / "e"), copy_main=False)
     empty.add_outputs(FakeOutputs(None))
     assert empty.write_summary() is None and not os.path.exists(tmp_path / "e" / "summary.txt")
+
+
+def test_tf_checkpoint_bundle_round_trip_and_corruption(tmp_path):
+    """tf.train.Saver's V2 bundle (.index SSTable + .data shard) written and read back without TensorFlow: many
+    tensors (several table blocks, prefix-compressed keys), scalars, float32 / float64 / int64, checksums."""
+    from cbf_ssm_b200.training import read_tf_checkpoint, reference_variable_names, write_tf_checkpoint
+    from cbf_ssm_b200.training.tf_checkpoint import crc32c
+    assert crc32c(b"123456789") == 0xE3069283                    # the CRC-32C check value
+    g = np.random.default_rng(0)
+    tensors = {"beta1_power": np.asarray(0.81), "global_step": np.asarray(7, dtype=np.int64)}
+    for i in range(150):
+        base = "Variable" if i == 0 else "Variable_%d" % i
+        shape = [(20, 6), (20, 4), (1,), (6,), ()][i % 5]
+        tensors[base] = g.standard_normal(shape)
+        tensors[base + "/Adam"] = g.standard_normal(shape).astype(np.float32)
+        tensors[base + "/Adam_1"] = g.standard_normal(shape)
+    tensors["kern/Variable"] = g.standard_normal((1,))
+    tensors["kern_1/Variable_1"] = g.standard_normal((6,))
+    prefix = str(tmp_path / "model.ckpt")
+    write_tf_checkpoint(prefix, tensors, block_size=512)
+    back = read_tf_checkpoint(prefix)
+    assert set(back) == set(tensors)
+    for k, v in tensors.items():
+        assert back[k].dtype == np.asarray(v).dtype and back[k].shape == np.asarray(v).shape and np.array_equal(back[k], v), k
+    # one flipped byte in the data shard / in the index is detected
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[100] ^= 1
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    with pytest.raises(ValueError, match="checksum"):
+        read_tf_checkpoint(prefix)
+    data[100] ^= 1
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[40] ^= 1
+    open(prefix + ".index", "wb").write(bytes(idx))
+    with pytest.raises(ValueError):
+        read_tf_checkpoint(prefix)
+    # the reference graph's default variable names, in creation order (gp_tf.py:112-127, cbfssm.py:30-54)
+    names = reference_variable_names()
+    assert [names[k] for k in ("f.zeta_pos", "f.zeta_mean", "f.zeta_var_unc", "f.variance_unc", "f.lengthscales_unc")] == \
+        ["Variable", "Variable_1", "Variable_2", "kern/Variable", "kern/Variable_1"]
+    assert [names[k] for k in ("b.zeta_pos", "b.variance_unc", "var_x_unc", "var_y_unc")] == \
+        ["Variable_3", "kern_1/Variable", "Variable_6", "Variable_7"]
+    assert reference_variable_names(half=True)["var_y_unc"] == "Variable_4"
