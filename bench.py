@@ -497,12 +497,17 @@ def run_b200(args):
                 "roofline": roofline_of(m, peaks, peaks_src, fp32_peak, traffic_table, key)}
 
     d = describe(main, args.workload)
+    kern_ms = sum(main["kms"][i] for i in range(6))
+    breakdown = {"rollout_and_accumulation_kernels_ms": kern_ms, "everything_else_ms": main["ms_per_step"] - kern_ms,
+                 "note": "everything else = normal draws, both float64 GP prologues and their adjoints, reductions, the "
+                         "all-reduce of the flat gradient (N > 1) and Adam; with few particles per GPU the rollout kernels do "
+                         "not shrink further because a time step is a serial chain (DESIGN.md 5.7, 7)"}
     line = {"metric": METRIC, "value": d["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": main["warm"], "ms_per_step": d["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64" if main.get("f64_path") else "f32", "data": "synthetic",
             "config": d["config"], "clocks": d["clocks"],
             "e2e": d["e2e"], "gpu_launches": d["gpu_launches"], "roofline": d["roofline"],
-            "l2_working_set_mib": d["l2_working_set_mib"],
+            "l2_working_set_mib": d["l2_working_set_mib"], "step_breakdown": breakdown,
             "fp32_fma_peak_measured_tflops": fp32_peak}
     if extra is not None:
         line["extra"] = {EXTRA: describe(extra, EXTRA)}
