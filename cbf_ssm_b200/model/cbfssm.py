@@ -150,10 +150,16 @@ class CBFSSM(BaseModel):
         else:
             c = self._draw_counter
             self._draw_counter += 1
-            sid = (c * 4 + 0) * 1024 + self.rank
-            self.engine.fill_normal(eb, self._draw_seed, sid)
-            self.engine.fill_normal(zb, self._draw_seed, sid + 1024)
-            self.engine.fill_normal(ef, self._draw_seed, sid + 2048)
+            sid = lambda slot: (c << 32) | (slot << 8) | (self.rank & 0xFF)     # Philox stream: (step, tensor / row, rank)
+            self.engine.fill_normal(eb, self._draw_seed, sid(0))
+            self.engine.fill_normal(ef, self._draw_seed, sid(1))
+            # z_b is read only where a run resamples (cbfssm.py:123-136: the random_normal sits inside the tf.cond
+            # branch), i.e. at 2 * ceil(T / 2R) of its 2T rows: draw just those rows
+            R = self.dims.recog_len
+            for run in (0, 1):
+                for t in range(T):
+                    if (t + (1 if run == 0 else R + 1)) % (2 * R) == 0:
+                        self.engine.fill_normal(zb[run, t], self._draw_seed, sid(2 + run * T + t))
         return eb, zb, ef
 
     def evaluate_batch(self, u_host, y_host, names, condition=True):
