@@ -146,7 +146,7 @@ struct AccLayout {
 // float64 state of one GP's prologue (cbf_gp_prologue): constrained parameters, K_zz, P = (K_zz + 1e-8 I)^-1,
 // alpha = P m, sigmoids for the adjoint, scratch.
 struct ProState {   // offsets (doubles) into the caller's state buffer
-  int64_t ell, sgl, sig2, sgv, S, sgS, m, Zt, K0, P, alpha, W1, W2, total;
+  int64_t ell, sgl, sig2, sgv, S, sgS, m, Zt, K0, P, alpha, W1, W2, cond, total;
   __host__ __device__ ProState(int M, int Din, int Dout) {
     int64_t o = 0;
     ell = o; o += Din;
@@ -163,6 +163,7 @@ struct ProState {   // offsets (doubles) into the caller's state buffer
     const int64_t w = (int64_t)M * (M > Din ? M : Din);   // scratch, also holds an [M, Din] temporary
     W1 = o; o += w;
     W2 = o; o += w;
+    cond = o; o += 1;      // 1-norm condition number of K_zz + 1e-8 I (diagnostic: float32 reaches ~1e3)
     total = o;
   }
 };

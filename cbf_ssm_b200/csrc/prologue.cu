@@ -142,6 +142,23 @@ __global__ void __launch_bounds__(512) gp_prologue_kernel(int M, int Din, int Do
   }
   const double total = block_sum_d(Dout * logdet + neg_half_log_s + 0.5 * (tr + quad), sh);
   if (tid == 0) kl_out[0] = total - 0.5 * (double)M * Dout;
+  // cond_1(K_zz + 1e-8 I) = ||K||_1 ||P||_1 (largest absolute column sums; both matrices are at hand)
+  double ck = 0.0, cp = 0.0;
+  for (int c = tid; c < M; c += nt) {
+    double sk = 1e-8, sp = 0.0;
+    for (int r = 0; r < M; ++r) { sk += fabs(K0[r * M + c]); sp += fabs(P[r * M + c]); }
+    ck = fmax(ck, sk); cp = fmax(cp, sp);
+  }
+  __syncthreads();
+  sh[tid] = ck;
+  __syncthreads();
+  for (int q = nt / 2; q > 0; q >>= 1) { if (tid < q) sh[tid] = fmax(sh[tid], sh[tid + q]); __syncthreads(); }
+  ck = sh[0];
+  __syncthreads();
+  sh[tid] = cp;
+  __syncthreads();
+  for (int q = nt / 2; q > 0; q >>= 1) { if (tid < q) sh[tid] = fmax(sh[tid], sh[tid + q]); __syncthreads(); }
+  if (tid == 0) st[o.cond] = ck * sh[0];
 }
 
 __global__ void __launch_bounds__(512) gp_prologue_backward_kernel(

@@ -267,6 +267,14 @@ class ElboEngine:
                                           ptr(g.Z), ptr(g.ell), ptr(g.sig2), ptr(g.P), ptr(g.alpha), ptr(g.S),
                                           ptr(g.kl), ptr(g.state), s2))
 
+    def cond_kzz(self):
+        """1-norm condition numbers of K_zz + 1e-8 I of the GPs as of the last prologue (synchronises).  The float32
+        rollout kernels hold 1e-4 against the float64 reference up to ~1e3."""
+        out = {}
+        for tag, g in (("f", self.gp_f),) + ((("b", self.gp_b),) if self.gp_b is not None else ()):
+            out[tag] = float(g.state[-1])      # ProState.cond is the last slot of the state buffer
+        return out
+
     def forward(self, u, y, eps_b, z_b, eps_f, condition=True, n_offset=0, n_local=None, run_prologue=True, x0=None,
                 predict_only=False):
         """u [B,T,du], y [B,T,dy] float32 device tensors; draws float32 device tensors

@@ -102,6 +102,21 @@ class CBFSSM(BaseModel):
         eng.adam_m.zero_()
         eng.adam_v.zero_()
         eng.adam_t = 0
+        self._warn_if_ill_conditioned()
+
+    def _warn_if_ill_conditioned(self):
+        """The float32 kernels form a = K_zz^-1 k with an explicit float32 inverse where the reference does float64
+        Cholesky solves; tell the user once if the initial inducing set is beyond their reach."""
+        eng = self.engine
+        if eng.flags & 128 or self.dims.ind_pnt_num > 128:
+            return
+        eng.prologue()
+        worst = max(eng.cond_kzz().values())
+        if worst > 1e4:
+            import warnings
+            warnings.warn("cond_1(K_zz) = %.1e at initialisation: the float32 rollout kernels are accuracy-limited for "
+                          "this inducing set (gradient errors ~ cond * 1e-7); set config['gpu_precision'] = 'float64'"
+                          % worst, RuntimeWarning, stacklevel=3)
 
     def state_dict(self):
         """Everything a checkpoint must hold: parameters and optimiser state (tf.train.Saver saves all global

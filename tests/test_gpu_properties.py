@@ -425,3 +425,30 @@ def test_reference_checkpoint_export_import_round_trip(tmp_path):
     assert len(loaded) == 12 * 3 + 1
     assert torch.equal(a.engine.theta, b.engine.theta) and torch.equal(a.engine.adam_m, b.engine.adam_m)
     assert torch.equal(a.engine.adam_v, b.engine.adam_v) and b.engine.adam_t == a.engine.adam_t == 3
+
+
+def test_condition_number_diagnostic_and_warning():
+    """The prologue leaves cond_1(K_zz + 1e-8 I) in its state; CBFSSM warns at initialisation when the float32
+    kernels cannot resolve the inducing set (M = 100 points in 3 input dims) and stays silent otherwise."""
+    import warnings
+    from cbf_ssm_b200.model import CBFSSM
+    eng = _engine(M=20)
+    eng.prologue()
+    torch.cuda.synchronize()
+    p = eng.get_params()
+    kern = O.RBF(torch.tensor(p["f.variance_unc"]), torch.tensor(p["f.lengthscales_unc"]))
+    K = kern.K(torch.tensor(p["f.zeta_pos"])).numpy() + 1e-8 * np.eye(20)
+    ref = np.linalg.norm(K, 1) * np.linalg.norm(np.linalg.inv(K), 1)
+    assert eng.cond_kzz()["f"] == pytest.approx(ref, rel=1e-6)
+
+    def cfg(dx, du, dy, M):
+        DS = type("DS", (), {"dim_u": du, "dim_y": dy})
+        return {'ds': DS, 'batch_size': 4, 'shuffle': 1, 'dim_x': dx, 'ind_pnt_num': M, 'samples': 8, 'learning_rate': 0.01,
+                'loss_factors': np.asarray([10., 0.]), 'k_factor': 1., 'recog_len': 6, 'zeta_pos': 2., 'zeta_mean': 0.01,
+                'zeta_var': 1e-4, 'var_x': np.full(dx, 0.01), 'var_y': np.full(dx, 1.0), 'gp_var': 0.01, 'gp_len': 1.}
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        CBFSSM(cfg(4, 2, 2, 100), seed=1)                      # cond ~ 10: silent
+        CBFSSM(dict(cfg(2, 1, 1, 100), gpu_precision="float64"), seed=1)
+    with pytest.warns(RuntimeWarning, match="accuracy-limited"):
+        CBFSSM(cfg(2, 1, 1, 100), seed=1)
