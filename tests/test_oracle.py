@@ -213,9 +213,10 @@ def test_reference_source_runs_here_and_matches_its_fixture():
     cfg, params, u, y, eb, zb, ef, cond = strong_ref_case(name)
     ref = RR.run_cbfssm(cfg, [params[k].numpy() for k in O.PARAM_NAMES], u, y, eb, zb, ef, cond)
     gold = np.load(os.path.join(GOLD, "ref_" + name + ".npz"))
-    assert float(ref["loss"]) == float(gold["loss"])
+    # (not bit-for-bit: the BLAS summation order may differ with the thread count of the machine running this)
+    assert float(ref["loss"]) == pytest.approx(float(gold["loss"]), rel=1e-12)
     for k, g in zip(O.PARAM_NAMES, ref["grads"]):
-        assert np.array_equal(g.reshape(gold["grad." + k].shape), gold["grad." + k]), k
+        assert rel_inf(g.reshape(gold["grad." + k].shape), gold["grad." + k]) < 1e-11, k
     # every draw the graph asked for came from the reference's own loop bodies
     bodies = {b for b, _, _, _ in ref["draw_log"]}
     assert bodies == {"_backward_body", "_forward_body"}
