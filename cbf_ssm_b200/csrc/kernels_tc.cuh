@@ -111,6 +111,16 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16], uint32_t (&q)[16
                :
                : "memory");
 }
+// 16 consecutive accumulator columns of this thread's TMEM lane written from registers.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :
+      : "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   tmem_ld16_issue(taddr, r);
@@ -148,7 +158,7 @@ struct TcCtx {
   static constexpr int XV = 1 + (2 * DOUT + 2) + DIN;   // exchange values per (group, particle): d2min | q, amax, fm, fv | x_bar
   static constexpr int MC = MC_;     // compile-time M (0: runtime) -- lets the M loops unroll and drop their guards
   static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
-  static constexpr uint32_t TMEM_COLS = REV ? 256u : 128u;
+  static constexpr uint32_t TMEM_COLS = 128u;   // one fp32 accumulator (MP <= 128 columns) per tile; the reverse pass reuses it
   __half *P1, *P2, *K1, *K2, *B1, *B2;
   const float *Zt, *al, *Sm, *il;
   float *xch;           // (NG > 1) [NG][XV][128] partial sums between the groups of a particle
@@ -271,10 +281,10 @@ struct TcCtx {
   }
 };
 
-// D[tmem_d] = A1 P1 + A2 P1 + A1 P2 for the tile's 128 rows; all threads of the tile call (contains the tile barrier
+// D[tmem_d] (+)= A1 P1 + A2 P1 + A1 P2 for the tile's 128 rows; all threads of the tile call (contains the tile barrier
 // and the mbarrier wait).  a1/a2: fp16 split A operands written by the threads just before.
 template <class Ctx>
-__device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __half *a2p, uint32_t tmem_d) {
+__device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __half *a2p, uint32_t tmem_d, uint32_t acc0 = 0) {
   async_proxy_fence();
   tc_fence_before();
   if (Ctx::NT == 1) __syncthreads(); else tile_sync(c.tile_id());
@@ -283,7 +293,7 @@ __device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __h
     const uint32_t lboA = kTcThreads * 16, lboB = c.MP * 16;
     const uint32_t a1 = smem_u32(a1p), a2 = smem_u32(a2p), b1 = smem_u32(c.P1), b2 = smem_u32(c.P2);
     const int ks = c.MP / 16;
-    uint32_t acc = 0;
+    uint32_t acc = acc0;   // 1: add to what the threads stored in the accumulator columns
     for (int pass = 0; pass < 3; ++pass) {
       const uint32_t ab = (pass == 1) ? a2 : a1, bb = (pass == 2) ? b2 : b1;
       for (int k = 0; k < ks; ++k) {
@@ -608,7 +618,10 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   int e2 = 0;
   frexpf(fmaxf(amax * cbound, 1e-30f), &e2);
   const float bsc = ldexpf(1.f, -e2), binv = ldexpf(1.f, e2);
-  const uint32_t trow1 = c.tmem + ((uint32_t)(t & ~31) << 16), trow2 = trow1 + 128;
+  const uint32_t trow1 = c.tmem + ((uint32_t)(t & ~31) << 16);
+  // k_bar needs 2 P b - 2 G a = 2 pbs (P' b'' + acoef a''): each thread overwrites its a'' row with acoef a'' once it
+  // has formed b'' from it, and the second contraction accumulates onto that -- one accumulator serves both products
+  const float acoef = -Gs * bsc / ps;
   if (live && g0 == 0) {
     o.template put_vec<DOUT>(o.bGm, gm);
     o.template put_vec<DOUT>(o.bGv, gv);
@@ -640,7 +653,9 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       const float at = ascale * a[e];
       bv[e] = a[e] * cm * bsc;
       a2[e] = at * at;
+      a[e] *= acoef;
     }
+    tmem_st16(trow1 + cc * 16, a);
     float lo[8], hi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { lo[e] = bv[e]; hi[e] = bv[8 + e]; }
@@ -653,11 +668,12 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       if (2 * cc + 1 < o.MB) o.put8(o.bA2 + 2 * cc + 1, hi);
     }
   }
+  tmem_st_wait();
   tc_fence_before();
   uint4 kq[4];   // raw hi/lo segments of two row-blocks of k' (one 16-row chunk), fetched one chunk ahead
   o.get8_raw(o.bK + 2 * g0, live, kq);
-  // ---- D2 = B P' ----
-  tc_contract(c, c.B1, c.B2, c.tmem + 128);
+  // ---- D <- acoef a'' + B P' ----
+  tc_contract(c, c.B1, c.B2, c.tmem, 1);
   // ---- k_bar = alpha gm + 2 P b - 2 G a ; w = k_bar k ; a_bar = 2 b - G k ----
   const float pbs = ps * ascale * binv;         // (P b)_m = pbs * (P' b'')_m
   const float bs = ascale * binv;               // b_m = bs * b''_m
@@ -670,11 +686,10 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   for (int j = 0; j < N2; ++j) { xs2[j] = 0ull; xs2b[j] = 0ull; }
 #pragma unroll(MC ? kTcChunkUnroll : 1)
   for (int cc = g0; cc < MP / 16; cc += NG) {
-    float pb[16], a[16], kp[16], bb[16];
+    float pb[16], kp[16], bb[16];
     {
-      uint32_t rp[16], ra[16];
-      tmem_ld16_issue(trow2 + cc * 16, rp);
-      tmem_ld16_issue(trow1 + cc * 16, ra);
+      uint32_t rp[16];
+      tmem_ld16_issue(trow1 + cc * 16, rp);
       // true k' of this chunk was fetched one iteration ahead; fetch the next chunk's now
       const uint4 c0 = kq[0], c1 = kq[1], c2 = kq[2], c3 = kq[3];
       if (cc + NG < MP / 16) o.get8_raw(o.bK + 2 * (cc + NG), live, kq);
@@ -686,9 +701,9 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
 #pragma unroll
         for (int e = 0; e < 8; ++e) { kp[e] = k0[e]; kp[8 + e] = k1[e]; }
       }
-      tmem_ld_wait(rp, ra);
+      tmem_ld_wait(rp);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) { pb[e] = __uint_as_float(rp[e]); a[e] = __uint_as_float(ra[e]); }
+      for (int e = 0; e < 16; ++e) pb[e] = __uint_as_float(rp[e]);
     }
     float wv[16], abv[16];
 #pragma unroll
@@ -696,7 +711,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       const int m = cc * 16 + e;
       float al[DOUTP];
       ld_row<DOUTP>(c.al + m * DOUTP, al);
-      float kb = 2.f * pbs * pb[e] - 2.f * Gs * ascale * a[e];
+      float kb = 2.f * pbs * pb[e];
 #pragma unroll
       for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gm[d], kb);
       const float k = sig2 * kp[e];
