@@ -158,6 +158,7 @@ struct TcCtx {
   static constexpr int XV = 1 + (2 * DOUT + 2) + DIN;   // exchange values per (group, particle): d2min | q, amax, fm, fv | x_bar
   static constexpr int MC = MC_;     // compile-time M (0: runtime) -- lets the M loops unroll and drop their guards
   static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
+  static constexpr uint32_t kTmemAlloc = NT <= 1 ? 128u : NT == 2 ? 256u : 512u;   // allocations are powers of two
   static constexpr uint32_t TMEM_COLS = 128u;   // one fp32 accumulator (MP <= 128 columns) per tile; the reverse pass reuses it
   __half *P1, *P2, *K1, *K2, *B1, *B2;
   const float *Zt, *al, *Sm, *il;
@@ -260,7 +261,7 @@ struct TcCtx {
     __syncwarp();
     if (tid < 32) {   // one warp allocates the TMEM columns (fp32 accumulators, 128 lanes x MP <= 128 per tile)
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemp)),
-                   "r"(TMEM_COLS * NT)
+                   "r"(kTmemAlloc)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -277,7 +278,7 @@ struct TcCtx {
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS * NT) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemAlloc) : "memory");
   }
 };
 
@@ -414,7 +415,8 @@ struct TcOut {
 };
 
 // One sparse-GP evaluation (gp_tf.py:132-161) for the CTA's 128 particles; every thread must call.
-// kout (optional): operand-tile column receiving k' for the outer-product GEMMs.
+// kout (optional): operand-tile column receiving the normalised k'' for the outer-product GEMMs (gp_reverse_tc
+// folds kscale into the partner operands a_bar and g_mean).
 // amax: max_m |a''_m| of this particle's normalised accumulator row (scales b in the reverse pass);
 // kscale: the particle's normalisation, k' = kscale * k''.
 // With NG groups (Ctx::NG > 1) a thread handles the 16-row chunks cc = grp, grp + NG, ...; every result
@@ -509,12 +511,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       kv[e] = kp;
     }
     tc_write_row8(c.K1, c.K2, t, ch, kv);
-    if (kout && ch < kout->MB) {
-      float ks[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) ks[e] = kscale * kv[e];
-      kout->put8(kout->bK + ch, ks);
-    }
+    if (kout && ch < kout->MB) kout->put8(kout->bK + ch, kv);   // the normalised k'': kscale goes into its partners
   }
   // ---- D1 = K P' on the tensor core ----
   tc_contract(c, c.K1, c.K2, c.tmem);
@@ -622,9 +619,17 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   // k_bar needs 2 P b - 2 G a = 2 pbs (P' b'' + acoef a''): each thread overwrites its a'' row with acoef a'' once it
   // has formed b'' from it, and the second contraction accumulates onto that -- one accumulator serves both products
   const float acoef = -Gs * bsc / ps;
+  // Per-particle factors are folded into the small operands and into loop constants instead of being applied per
+  // inducing row: the K operand holds k'' (k' = kscale k''), the A2 operand a''^2 (a = ascale a'').
+  float gvs[DOUT], gms[DOUT];
+#pragma unroll
+  for (int d = 0; d < DOUT; ++d) { gvs[d] = gv[d] * bsc; gms[d] = gm[d] * (sig2 * kscale); }
   if (live && g0 == 0) {
-    o.template put_vec<DOUT>(o.bGm, gm);
-    o.template put_vec<DOUT>(o.bGv, gv);
+    float gmk[DOUT], gva[DOUT];
+#pragma unroll
+    for (int d = 0; d < DOUT; ++d) { gmk[d] = gm[d] * kscale; gva[d] = gv[d] * (ascale * ascale); }
+    o.template put_vec<DOUT>(o.bGm, gmk);
+    o.template put_vec<DOUT>(o.bGv, gva);
     float x1[DIN + 1];
 #pragma unroll
     for (int j = 0; j < DIN; ++j) x1[j] = xt[j];
@@ -649,10 +654,9 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       ld_row<DOUTP>(c.Sm + m * DOUTP, S);
       float cm = 0.f;
 #pragma unroll
-      for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], gv[d], cm);
-      const float at = ascale * a[e];
-      bv[e] = a[e] * cm * bsc;
-      a2[e] = at * at;
+      for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], gvs[d], cm);
+      bv[e] = a[e] * cm;
+      a2[e] = a[e] * a[e];
       a[e] *= acoef;
     }
     tmem_st16(trow1 + cc * 16, a);
@@ -677,6 +681,8 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   // ---- k_bar = alpha gm + 2 P b - 2 G a ; w = k_bar k ; a_bar = 2 b - G k ----
   const float pbs = ps * ascale * binv;         // (P b)_m = pbs * (P' b'')_m
   const float bs = ascale * binv;               // b_m = bs * b''_m
+  const float kfac = sig2 * kscale;             // k_m = kfac * k''_m
+  const float c_pb = 2.f * pbs * kfac, c_bb = 2.f * bs * kscale, c_k = -Gs * kfac * kscale;
   constexpr int J2 = (DIN + 1) / 2, N2 = (NEED + 1) / 2;
   unsigned long long x2[J2], xs2[N2], L2[J2], xs2b[N2], L2b[J2];   // packed over input-dim pairs (2j, 2j+1); two chains (even / odd rows)
   float swb = 0.f;
@@ -690,7 +696,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     {
       uint32_t rp[16];
       tmem_ld16_issue(trow1 + cc * 16, rp);
-      // true k' of this chunk was fetched one iteration ahead; fetch the next chunk's now
+      // k'' of this chunk was fetched one iteration ahead; fetch the next chunk's now
       const uint4 c0 = kq[0], c1 = kq[1], c2 = kq[2], c3 = kq[3];
       if (cc + NG < MP / 16) o.get8_raw(o.bK + 2 * (cc + NG), live, kq);
       tc_read_row16(c.B1, c.B2, t, cc, bb);
@@ -711,11 +717,10 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       const int m = cc * 16 + e;
       float al[DOUTP];
       ld_row<DOUTP>(c.al + m * DOUTP, al);
-      float kb = 2.f * pbs * pb[e];
+      float kb = c_pb * pb[e];                  // kfac * k_bar
 #pragma unroll
-      for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gm[d], kb);
-      const float k = sig2 * kp[e];
-      const float w = kb * k;
+      for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gms[d], kb);
+      const float w = kb * kp[e];
       if (e & 1) swb += w; else sw += w;
       float z[DINP];
       ld_row<DINP>(c.Zt + m * DINP, z);
@@ -733,7 +738,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
         }
       }
       wv[e] = w;
-      abv[e] = 2.f * bs * bb[e] - Gs * k;
+      abv[e] = fmaf(c_k, kp[e], c_bb * bb[e]);  // kscale * a_bar (its partner operand holds k'')
     }
     if (live) {
       float lo[8], hi[8];
@@ -1243,6 +1248,10 @@ struct LaunchTc {
   // the GPU has SMs, i.e. when the serial chain of a time step, not throughput, sets the kernel's duration
   static constexpr bool kSplit = DX <= 4;
   static constexpr int kSplitG = 2;
+  // small dims at M <= 112: three tiles sharing P fit one SM's shared memory (12 warps per SM instead of the 8 of two
+  // one-tile CTAs); used when the launch fills whole waves of them better (want_tri)
+  static constexpr bool kTri = !kDual && DX <= 4;
+  static constexpr int kMulti = kDual ? 2 : (kTri ? 3 : 1);
   static constexpr size_t kMaxDyn = 227 * 1024;
   static size_t smem_b(int M) { return TcCtx<DIN, DH>::bytes(M); }
   static size_t smem_f(int M) { return TcCtx<DIN, DX>::bytes(M); }
@@ -1265,6 +1274,18 @@ struct LaunchTc {
     return ctas <= sm_count();
   }
 
+  // Three-tile CTAs when the estimated makespan is shorter: a wave of them (3 tiles per SM) takes kTriSlow times a wave
+  // of one-tile CTAs (2 tiles per SM; measured 1.48 at M = 100), and a launch takes whole waves of either kind.
+  static constexpr float kTriSlow = 1.48f;
+  static bool want_tri(int tiles, int nchain) {
+    const char *e = getenv("CBFSSM_B200_TC_TILES");      // 1: never, 3: always (tests, measurement), unset: by launch size
+    if (e != nullptr && *e) return atoi(e) == 3;
+    const int sms = sm_count();
+    const float w1 = (float)ceil_div(tiles * nchain, 2 * sms);
+    const float w3 = kTriSlow * (float)ceil_div(ceil_div(tiles, 3) * nchain, sms);
+    return w3 < w1;
+  }
+
   // Launch `k1` (one particle tile per CTA), or `ks` (one tile, kSplitG threads per particle) when the launch is
   // latency-bound, or, when only one one-tile CTA fits an SM and the two-tile CTA fits at all, `k2` (two tiles
   // sharing P and the tables).  `launch(kernel, grid_x, threads, smem)` enqueues.
@@ -1277,6 +1298,16 @@ struct LaunchTc {
         e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems);
         if (e != cudaSuccess) return e;
         launch(ks, tiles, kSplitG * kTcThreads, smems);
+        return cudaGetLastError();
+      }
+    }
+    if constexpr (kTri) {
+      cudaFuncAttributes fa;
+      if ((e = cudaFuncGetAttributes(&fa, k2)) != cudaSuccess) return e;
+      if (smem2 + fa.sharedSizeBytes <= kMaxDyn && want_tri(tiles, nchain)) {
+        e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return e;
+        launch(k2, ceil_div(tiles, 3), 3 * kTcThreads, smem2);
         return cudaGetLastError();
       }
     }
@@ -1304,14 +1335,14 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, w_ll, w_kl, ws, mats, win, spart, nsc); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DX, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, true, 0, 2>::bytes(D.M),
+    const size_t s1 = TcCtx<DIN, DX, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, true, 0, kMulti>::bytes(D.M),
                  ss = TcCtx<DIN, DX, true, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(fw_reverse_tc_kernel<DX, DU, DY, 100, 1>, fw_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+        return pick(fw_reverse_tc_kernel<DX, DU, DY, 100, 1>, fw_reverse_tc_kernel<DX, DU, DY, 100, kMulti>,
                     fw_reverse_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, 1, launch);
     }
-    return pick(fw_reverse_tc_kernel<DX, DU, DY, 0, 1>, fw_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+    return pick(fw_reverse_tc_kernel<DX, DU, DY, 0, 1>, fw_reverse_tc_kernel<DX, DU, DY, 0, kMulti>,
                 fw_reverse_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, 1, launch);
   }
   static cudaError_t bm_reverse(const Dims &D, const ChainTable &ct, GpDev gp, const float *vx, const float *u,
@@ -1321,14 +1352,14 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, w_en, ws, mats, spart, nsc); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DH, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, true, 0, 2>::bytes(D.M),
+    const size_t s1 = TcCtx<DIN, DH, true, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, true, 0, kMulti>::bytes(D.M),
                  ss = TcCtx<DIN, DH, true, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(bm_reverse_tc_kernel<DX, DU, DY, 100, 1>, bm_reverse_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+        return pick(bm_reverse_tc_kernel<DX, DU, DY, 100, 1>, bm_reverse_tc_kernel<DX, DU, DY, 100, kMulti>,
                     bm_reverse_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
     }
-    return pick(bm_reverse_tc_kernel<DX, DU, DY, 0, 1>, bm_reverse_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+    return pick(bm_reverse_tc_kernel<DX, DU, DY, 0, 1>, bm_reverse_tc_kernel<DX, DU, DY, 0, kMulti>,
                 bm_reverse_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
   }
 
@@ -1339,14 +1370,14 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<dim3(gx, ct.count), threads, smem, st>>>(D, ct, gp, vx, u, y, eps_b, z_b, ws, part_out); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DH, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, false, 0, 2>::bytes(D.M),
+    const size_t s1 = TcCtx<DIN, DH, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DH, false, 0, kMulti>::bytes(D.M),
                  ss = TcCtx<DIN, DH, false, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(bm_forward_tc_kernel<DX, DU, DY, 100, 1>, bm_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+        return pick(bm_forward_tc_kernel<DX, DU, DY, 100, 1>, bm_forward_tc_kernel<DX, DU, DY, 100, kMulti>,
                     bm_forward_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
     }
-    return pick(bm_forward_tc_kernel<DX, DU, DY, 0, 1>, bm_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+    return pick(bm_forward_tc_kernel<DX, DU, DY, 0, 1>, bm_forward_tc_kernel<DX, DU, DY, 0, kMulti>,
                 bm_forward_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, ct.count, launch);
   }
   static cudaError_t fw_forward(const Dims &D, GpDev gp, const float *vx, const float *vy, const float *u,
@@ -1355,14 +1386,14 @@ struct LaunchTc {
     auto launch = [&](auto kernel, int gx, int threads, size_t smem) {
       kernel<<<gx, threads, smem, st>>>(D, gp, vx, vy, u, y, eps_f, ws, part_out); cbf_note_launch();
     };
-    const size_t s1 = TcCtx<DIN, DX, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, false, 0, 2>::bytes(D.M),
+    const size_t s1 = TcCtx<DIN, DX, false, 0, 1>::bytes(D.M), s2 = TcCtx<DIN, DX, false, 0, kMulti>::bytes(D.M),
                  ss = TcCtx<DIN, DX, false, 0, 1, G>::bytes(D.M);
     if constexpr (kHas100) {
       if (D.M == 100)
-        return pick(fw_forward_tc_kernel<DX, DU, DY, 100, 1>, fw_forward_tc_kernel<DX, DU, DY, 100, kDual ? 2 : 1>,
+        return pick(fw_forward_tc_kernel<DX, DU, DY, 100, 1>, fw_forward_tc_kernel<DX, DU, DY, 100, kMulti>,
                     fw_forward_tc_kernel<DX, DU, DY, 100, 1, G>, s1, s2, ss, D.n_local, 1, launch);
     }
-    return pick(fw_forward_tc_kernel<DX, DU, DY, 0, 1>, fw_forward_tc_kernel<DX, DU, DY, 0, kDual ? 2 : 1>,
+    return pick(fw_forward_tc_kernel<DX, DU, DY, 0, 1>, fw_forward_tc_kernel<DX, DU, DY, 0, kMulti>,
                 fw_forward_tc_kernel<DX, DU, DY, 0, 1, G>, s1, s2, ss, D.n_local, 1, launch);
   }
 };

@@ -180,20 +180,24 @@ def test_tensor_path_time_windows_match_oracle(shape, budget, monkeypatch):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("split", ["0", "1"], ids=["one_thread_per_particle", "four_threads_per_particle"])
+@pytest.mark.parametrize("split", ["0", "1", "tiles3"],
+                         ids=["one_thread_per_particle", "two_threads_per_particle", "three_tiles_per_cta"])
 @pytest.mark.parametrize("case", [
     (4, 1, 1, 100, 10, 2, 30, 10, 1.0, (10.0, 0.0), True, False),        # M = 100 compile-time instantiation
     (4, 2, 2, 100, 16, 8, 40, 10, 1.0, (10.0, 0.3), True, True),
     (4, 2, 2, 128, 20, 7, 12, 4, 1.0, (10.0, 0.3), True, True),          # runtime M, 8 chunks: 2 per group
     (4, 1, 1, 24, 40, 2, 20, 4, 1.0, (10.0, 1.0), False, True),          # 2 chunks: groups 2, 3 own no rows
     (3, 1, 1, 40, 37, 5, 13, 3, 3.0, (6.0, 1.0), True, True),            # 3 chunks, 2 ragged tiles
+    (4, 2, 2, 100, 50, 11, 12, 4, 1.0, (10.0, 0.5), True, True),         # 5 tiles: a full and a partly filled 3-tile CTA
 ], ids=lambda c: "dx%d_du%d_dy%d_M%d_S%d_B%d_T%d_R%d" % c[:8])
 def test_tensor_path_latency_variant_matches_oracle(case, split, monkeypatch):
-    """The tensor path has a latency variant (4 threads per particle, each a quarter of the M rows; chosen when a
-    launch has fewer CTAs than the GPU has SMs) besides the throughput variant (1 thread per particle).  Every parity
-    case in this file is small enough to get the former by default; this test forces each variant in turn, also
-    through the time-window machinery."""
-    monkeypatch.setenv("CBFSSM_B200_TC_SPLIT", split)
+    """The tensor path has a latency variant (2 threads per particle, each half of the M rows; chosen when a launch
+    has fewer CTAs than the GPU has SMs) besides the throughput variants (1 thread per particle; one particle tile
+    per CTA, or three tiles sharing P where that fills whole waves better).  Every parity case in this file is small
+    enough to get the first by default; this test forces each variant in turn, also through the time-window
+    machinery."""
+    monkeypatch.setenv("CBFSSM_B200_TC_SPLIT", "0" if split == "tiles3" else split)
+    monkeypatch.setenv("CBFSSM_B200_TC_TILES", "3" if split == "tiles3" else "1")
     dx, du, dy, M, S, B, T, R, kap, lf, cond, strong = case
     cfg, params, u, y, eps_b, z_b, eps_f = make_problem(dx, du, dy, M, S, B, T, R, kap, lf, seed=17, strong=strong)
     res, gd = O.loss_and_grads(cfg, params, u, y, eps_b, z_b, eps_f, cond)
