@@ -706,9 +706,13 @@ __global__ void fill_normal_kernel(float *__restrict__ out, int64_t n, uint64_t 
     z[2 * h] = rr * cs;
     z[2 * h + 1] = rr * sn;
   }
+  if (q * 4 + 3 < n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {   // one 16-byte store per thread: full sectors
+    *reinterpret_cast<float4 *>(out + q * 4) = make_float4(z[0], z[1], z[2], z[3]);
+  } else {
 #pragma unroll
-  for (int h = 0; h < 4; ++h)
-    if (q * 4 + h < n) out[q * 4 + h] = z[h];
+    for (int h = 0; h < 4; ++h)
+      if (q * 4 + h < n) out[q * 4 + h] = z[h];
+  }
 }
 
 static int device_sms() {
