@@ -101,6 +101,43 @@ def test_elbo_and_gradients_match_oracle(case, flags):
     assert not bad, bad
 
 
+def _random_cases(count, seed):
+    """Seeded random shapes over the compiled (dx, du, dy) triples: ragged tiles, R above and below T, one-particle
+    and one-sequence batches, both branches of `condition`."""
+    rng = np.random.RandomState(seed)
+    dims = [(4, 2, 2), (4, 1, 1), (14, 7, 7), (13, 6, 7), (2, 1, 1), (8, 1, 4), (16, 1, 8), (3, 1, 1)]
+    out = []
+    for _ in range(count):
+        dx, du, dy = dims[rng.randint(len(dims))]
+        m_hi = 14 if dx + du <= 4 else 48          # few input dims: keep the inducing set well conditioned for float32
+        M = int(rng.randint(2, m_hi + 1))
+        S, B, T = int(rng.randint(1, 41)), int(rng.randint(1, 7)), int(rng.randint(2, 25))
+        R = int(rng.randint(1, 31))
+        kap = float(rng.choice([1.0, 2.0, 10.0, 50.0]))
+        lf = (float(rng.choice([6.0, 10.0, 20.0])), float(rng.choice([0.0, 0.3, 1.0])))
+        out.append((dx, du, dy, M, S, B, T, R, kap, lf, bool(rng.rand() < 0.75), True))
+    return out
+
+
+@pytest.mark.parametrize("flags", [0, 12], ids=["default_dispatch", "register_or_tensor"])
+@pytest.mark.parametrize("case", _random_cases(14, seed=20261018), ids=lambda c: "dx%d_du%d_dy%d_M%d_S%d_B%d_T%d_R%d" % c[:8])
+def test_random_shapes_match_oracle(case, flags):
+    dx, du, dy, M, S, B, T, R, kap, lf, cond, strong = case
+    cfg, params, u, y, eps_b, z_b, eps_f = make_problem(dx, du, dy, M, S, B, T, R, kap, lf, seed=101, strong=strong)
+    res, gd = O.loss_and_grads(cfg, params, u, y, eps_b, z_b, eps_f, cond)
+    eng, out, yd = run_engine(cfg, params, u, y, eps_b, z_b, eps_f, cond, flags)
+    for k in ("loss", "loglik", "kl_x", "entropy", "kl_z_f", "kl_z_b"):
+        ref, got = float(getattr(res, k).detach()), float(out[k])
+        assert abs(got - ref) <= TOL * max(abs(ref), 1e-3), (k, got, ref)
+    xf, yt = eng.export_states(yd)
+    assert rel_inf(xf.cpu().numpy(), res.x_final.detach().numpy()) < TOL
+    assert rel_inf(yt.cpu().numpy(), res.y_tilde.detach().numpy()) < TOL
+    grads = eng.get_grads()
+    bad = {k: rel_inf(grads[k], gd[k].numpy()) for k in O.PARAM_NAMES}
+    bad = {k: v for k, v in bad.items() if not v < TOL}
+    assert not bad, bad
+
+
 def _f32_exact(*arrays):
     """The C ABI takes u, y and the draws as float32.  For ill-conditioned inducing sets the *problem* is sensitive to
     that rounding (the float64 oracle's own gradients move by up to 1e-2 at cond 1e9 when its inputs are rounded), so
