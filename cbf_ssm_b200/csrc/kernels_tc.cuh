@@ -621,9 +621,14 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   const float acoef = -Gs * bsc / ps;
   // Per-particle factors are folded into the small operands and into loop constants instead of being applied per
   // inducing row: the K operand holds k'' (k' = kscale k''), the A2 operand a''^2 (a = ascale a'').
-  float gvs[DOUT], gms[DOUT];
+  // (pre-scaled copies of gm / gv only for few output dims: at DOUT = 14 the 28 extra live registers cost more than
+  // the two multiplies per row they save -- measured +6 % on the Sarcos shape)
+  constexpr bool kPre = DOUT <= 4;
+  float gvs[kPre ? DOUT : 1], gms[kPre ? DOUT : 1];
+  if constexpr (kPre) {
 #pragma unroll
-  for (int d = 0; d < DOUT; ++d) { gvs[d] = gv[d] * bsc; gms[d] = gm[d] * (sig2 * kscale); }
+    for (int d = 0; d < DOUT; ++d) { gvs[d] = gv[d] * bsc; gms[d] = gm[d] * (sig2 * kscale); }
+  }
   if (live && g0 == 0) {
     float gmk[DOUT], gva[DOUT];
 #pragma unroll
@@ -654,8 +659,8 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       ld_row<DOUTP>(c.Sm + m * DOUTP, S);
       float cm = 0.f;
 #pragma unroll
-      for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], gvs[d], cm);
-      bv[e] = a[e] * cm;
+      for (int d = 0; d < DOUT; ++d) cm = fmaf(S[d], kPre ? gvs[kPre ? d : 0] : gv[d], cm);
+      bv[e] = kPre ? a[e] * cm : a[e] * (cm * bsc);
       a2[e] = a[e] * a[e];
       a[e] *= acoef;
     }
@@ -717,9 +722,17 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       const int m = cc * 16 + e;
       float al[DOUTP];
       ld_row<DOUTP>(c.al + m * DOUTP, al);
-      float kb = c_pb * pb[e];                  // kfac * k_bar
+      float kb;                                 // kfac * k_bar
+      if constexpr (kPre) {
+        kb = c_pb * pb[e];
 #pragma unroll
-      for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gms[d], kb);
+        for (int d = 0; d < DOUT; ++d) kb = fmaf(al[d], gms[d], kb);
+      } else {
+        float dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < DOUT; ++d) dot = fmaf(al[d], gm[d], dot);
+        kb = fmaf(c_pb, pb[e], kfac * dot);
+      }
       const float w = kb * kp[e];
       if (e & 1) swb += w; else sw += w;
       float z[DINP];
