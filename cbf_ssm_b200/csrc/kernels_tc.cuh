@@ -441,11 +441,16 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   constexpr int J2 = (DIN + 1) / 2, D2 = (DOUT + 1) / 2;
   // Every sum over the inducing rows runs as two interleaved chains (even / odd rows): with two warps per
   // scheduler a single 16-long dependent FMA chain per chunk leaves the issue slot idle for its latency.
-  unsigned long long x2[J2], fm2[D2], fv2[D2], fm2b[D2], fv2b[D2];
+  // (only for few dims: at DIN = 21 / DOUT = 14 the second set of accumulators spills)
+  constexpr bool kTwo = DIN <= 8;
+  constexpr int D2b = kTwo ? D2 : 1;
+  unsigned long long x2[J2], fm2[D2], fv2[D2], fm2b[D2b], fv2b[D2b];
 #pragma unroll
   for (int j = 0; j < J2; ++j) x2[j] = pack2(xt[2 * j], xt[2 * j + 1]);   // xt is zero-padded to DINP
 #pragma unroll
-  for (int d = 0; d < D2; ++d) { fm2[d] = 0ull; fv2[d] = 0ull; fm2b[d] = 0ull; fv2b[d] = 0ull; }
+  for (int d = 0; d < D2; ++d) { fm2[d] = 0ull; fv2[d] = 0ull; }
+#pragma unroll
+  for (int d = 0; d < D2b; ++d) { fm2b[d] = 0ull; fv2b[d] = 0ull; }
   // ---- kernel vector -> fp16 split operands ----
   // fp16 has a narrow exponent range and k' = exp(-d^2/2) can be 1e-12 for every inducing point (e.g.
   // 21 input dims), so each particle's vector is normalised by its own maximum: pass 1 parks the squared
@@ -470,7 +475,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
         acc = fma2(dl, dl, acc);
       }
       const float d2 = hsum2(acc);
-      if (e & 1) d2minb = fminf(d2minb, d2); else d2min = fminf(d2min, d2);
+      if (kTwo && (e & 1)) d2minb = fminf(d2minb, d2); else d2min = fminf(d2min, d2);
       dv[e] = d2;
     }
     const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
@@ -504,7 +509,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
         const unsigned long long kk = pack2(kp, kp);
 #pragma unroll
         for (int d = 0; d < D2; ++d) {
-          if (e & 1) fm2b[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2b[d]);
+          if (kTwo && (e & 1)) fm2b[kTwo ? d : 0] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2b[kTwo ? d : 0]);
           else fm2[d] = fma2(pack2(al[2 * d], al[2 * d + 1]), kk, fm2[d]);
         }
       }
@@ -540,11 +545,11 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       float S[DOUTP];
       ld_row<DOUTP>(c.Sm + m * DOUTP, S);
       const unsigned long long aa = pack2(a2, a2);
-      if (e & 1) {
+      if (kTwo && (e & 1)) {
         qb = fmaf(kp[e], a[e], qb);
         amaxb = fmaxf(amaxb, fabsf(a[e]));
 #pragma unroll
-        for (int d = 0; d < D2; ++d) fv2b[d] = fma2(pack2(S[2 * d], S[2 * d + 1]), aa, fv2b[d]);
+        for (int d = 0; d < D2b; ++d) fv2b[d] = fma2(pack2(S[2 * d], S[2 * d + 1]), aa, fv2b[d]);
       } else {
         q = fmaf(kp[e], a[e], q);
         amax = fmaxf(amax, fabsf(a[e]));
@@ -557,8 +562,10 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   amax = fmaxf(amax, amaxb);
 #pragma unroll
   for (int d = 0; d < D2; ++d) {
-    fm2[d] = add2(fm2[d], fm2b[d]);
-    fv2[d] = add2(fv2[d], fv2b[d]);
+    if (kTwo) {
+      fm2[d] = add2(fm2[d], fm2b[kTwo ? d : 0]);
+      fv2[d] = add2(fv2[d], fv2b[kTwo ? d : 0]);
+    }
     float m0, m1, v0, v1;
     unpack2(fm2[d], m0, m1);
     unpack2(fv2[d], v0, v1);
@@ -689,12 +696,18 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   const float kfac = sig2 * kscale;             // k_m = kfac * k''_m
   const float c_pb = 2.f * pbs * kfac, c_bb = 2.f * bs * kscale, c_k = -Gs * kfac * kscale;
   constexpr int J2 = (DIN + 1) / 2, N2 = (NEED + 1) / 2;
-  unsigned long long x2[J2], xs2[N2], L2[J2], xs2b[N2], L2b[J2];   // packed over input-dim pairs (2j, 2j+1); two chains (even / odd rows)
+  constexpr bool kTwo = DIN <= 8;   // two chains (even / odd rows) only where the second set of accumulators fits the registers
+  constexpr int N2b = kTwo ? N2 : 1, J2b = kTwo ? J2 : 1;
+  unsigned long long x2[J2], xs2[N2], L2[J2], xs2b[N2b], L2b[J2b];   // packed over input-dim pairs (2j, 2j+1)
   float swb = 0.f;
 #pragma unroll
-  for (int j = 0; j < J2; ++j) { x2[j] = pack2(xt[2 * j], xt[2 * j + 1]); L2[j] = 0ull; L2b[j] = 0ull; }
+  for (int j = 0; j < J2; ++j) { x2[j] = pack2(xt[2 * j], xt[2 * j + 1]); L2[j] = 0ull; }
 #pragma unroll
-  for (int j = 0; j < N2; ++j) { xs2[j] = 0ull; xs2b[j] = 0ull; }
+  for (int j = 0; j < J2b; ++j) L2b[j] = 0ull;
+#pragma unroll
+  for (int j = 0; j < N2; ++j) xs2[j] = 0ull;
+#pragma unroll
+  for (int j = 0; j < N2b; ++j) xs2b[j] = 0ull;
 #pragma unroll(MC ? kTcChunkUnroll : 1)
   for (int cc = g0; cc < MP / 16; cc += NG) {
     float pb[16], kp[16], bb[16];
@@ -734,7 +747,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
         kb = fmaf(c_pb, pb[e], kfac * dot);
       }
       const float w = kb * kp[e];
-      if (e & 1) swb += w; else sw += w;
+      if (kTwo && (e & 1)) swb += w; else sw += w;
       float z[DINP];
       ld_row<DINP>(c.Zt + m * DINP, z);
       const unsigned long long ww = pack2(w, w);
@@ -742,9 +755,9 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       for (int j = 0; j < J2; ++j) {
         const unsigned long long dl = add2(x2[j], pack2(z[2 * j], z[2 * j + 1]));
         const unsigned long long wd = mul2(dl, ww);
-        if (e & 1) {
-          if (j < N2) xs2b[j < N2 ? j : 0] = add2(xs2b[j < N2 ? j : 0], wd);
-          L2b[j] = fma2(wd, dl, L2b[j]);
+        if (kTwo && (e & 1)) {
+          if (j < N2) xs2b[(kTwo && j < N2) ? j : 0] = add2(xs2b[(kTwo && j < N2) ? j : 0], wd);
+          L2b[kTwo ? j : 0] = fma2(wd, dl, L2b[kTwo ? j : 0]);
         } else {
           if (j < N2) xs2[j < N2 ? j : 0] = add2(xs2[j < N2 ? j : 0], wd);
           L2[j] = fma2(wd, dl, L2[j]);
@@ -767,10 +780,10 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   }
   sw += swb;
 #pragma unroll
-  for (int j = 0; j < N2; ++j) xs2[j] = add2(xs2[j], xs2b[j]);
+  for (int j = 0; j < N2b; ++j) if (kTwo) xs2[j] = add2(xs2[j], xs2b[j]);
 #pragma unroll
   for (int j = 0; j < J2; ++j) {
-    L2[j] = add2(L2[j], L2b[j]);
+    if (kTwo) L2[j] = add2(L2[j], L2b[kTwo ? j : 0]);
     float l0, l1;
     unpack2(L2[j], l0, l1);
     Lacc[2 * j] += l0;
