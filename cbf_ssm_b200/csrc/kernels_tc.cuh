@@ -194,6 +194,12 @@ struct TcCtx {
     // The reverse pass reuses the K operand buffers for b (k is re-read from the float32 operand
     // matrix it was just written to, an L2 hit), which keeps the CTA at ~114 KB: two CTAs per SM.
     B1 = K1; B2 = K2;
+    {   // every row group the kernels visit is rewritten each evaluation; a padding group they skip (for_chunks) must
+        // read as zeros in the contractions, so the buffers start zeroed
+      uint4 *kz = reinterpret_cast<uint4 *>(base - (size_t)NT * 2 * kTcThreads * MP * 2);
+      const int n16 = (int)((size_t)NT * 2 * kTcThreads * MP * 2 / 16);
+      for (int i = threadIdx.x; i < n16; i += blockDim.x) kz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     // The tables have MP rows (Zt holds -Z/ell so that delta is one packed add): rows >= M hold Z/ell = 1e18 (squared distance ~1e37, so k'' underflows to an
     // exact 0 and never wins the minimum) and alpha = S = 0, which makes every padded row contribute exact
     // zeros everywhere -- the per-row loops need no m < M guards.
@@ -309,10 +315,28 @@ __device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __h
   tc_fence_after();
 }
 
-// This thread's row (16 fp16-split values starting at column 16*cc) of an A-operand buffer pair.
+// The 16-row chunks cc = g0, g0 + NG, ... of an M-vector.  With a compile-time M whose last chunk has at most 8 live
+// rows (M = 100: rows 96..99) that chunk is visited as ONE 8-row group (Rows<8>): its second group is all padding,
+// the operand buffers keep the zeros they were initialised with there, and 8 of 112 rows of per-row work go away.
+template <int N> struct Rows { static constexpr int value = N; };
+template <int MC, int NG, class F>
+__device__ __forceinline__ void for_chunks(int g0, int nch, F &&body) {
+  constexpr bool kTail = MC > 0 && (MC % 16) >= 1 && (MC % 16) <= 8;
+  if constexpr (kTail) {
+#pragma unroll 1
+    for (int cc = g0; cc < nch - 1; cc += NG) body(cc, Rows<16>{});
+    if (NG == 1 || (nch - 1) % NG == g0) body(nch - 1, Rows<8>{});
+  } else {
+#pragma unroll 1
+    for (int cc = g0; cc < nch; cc += NG) body(cc, Rows<16>{});
+  }
+}
+
+// This thread's row (ROWS fp16-split values starting at column 16*cc) of an A-operand buffer pair.
+template <int ROWS = 16>
 __device__ __forceinline__ void tc_read_row16(const __half *b1, const __half *b2, int row, int cc, float (&v)[16]) {
 #pragma unroll
-  for (int hch = 0; hch < 2; ++hch) {
+  for (int hch = 0; hch < ROWS / 8; ++hch) {
     const size_t off = (size_t)(cc * 2 + hch) * (kTcThreads * 8) + row * 8;
     const uint4 v1 = *reinterpret_cast<const uint4 *>(b1 + off);
     const uint4 v2 = *reinterpret_cast<const uint4 *>(b2 + off);
@@ -457,10 +481,9 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   // distances (float32) in the thread's own K1/K2 slots and finds their minimum, pass 2 forms
   // k'' = exp(-(d^2 - d^2_min)/2) in (0,1] (max exactly 1), splits and overwrites.  k' = kscale * k''.
   float d2min = 3.0e38f, d2minb = 3.0e38f;
-#pragma unroll 1
-  for (int cc = g0; cc < MP / 16; cc += NG)
+  for_chunks<MC, NG>(g0, MP / 16, [&](const int cc, auto rows_tag) {
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {   // 8-row chunks 2cc, 2cc+1 of the own 16-row chunks cc
+  for (int hh = 0; hh < decltype(rows_tag)::value / 8; ++hh) {   // 8-row chunks 2cc, 2cc+1 of the own 16-row chunks cc
     const int ch = 2 * cc + hh;
     float dv[8];
 #pragma unroll
@@ -482,6 +505,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
     *reinterpret_cast<float4 *>(c.K1 + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
     *reinterpret_cast<float4 *>(c.K2 + off) = make_float4(dv[4], dv[5], dv[6], dv[7]);
   }
+  });
   d2min = fminf(d2min, d2minb);
   if (NG > 1) {   // the particle's minimum over all groups
     *c.xslot(g0, 0) = d2min;
@@ -490,10 +514,9 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
     for (int g = 0; g < NG; ++g) d2min = fminf(d2min, *c.xslot(g, 0));
   }
   kscale = fast_exp2(kNegHalfLog2e * d2min);
-#pragma unroll 1
-  for (int cc = g0; cc < MP / 16; cc += NG)
+  for_chunks<MC, NG>(g0, MP / 16, [&](const int cc, auto rows_tag) {
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
+  for (int hh = 0; hh < decltype(rows_tag)::value / 8; ++hh) {
     const int ch = 2 * cc + hh;
     const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
     const float4 da = *reinterpret_cast<const float4 *>(c.K1 + off), db = *reinterpret_cast<const float4 *>(c.K2 + off);
@@ -518,6 +541,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
     tc_write_row8(c.K1, c.K2, t, ch, kv);
     if (kout && ch < kout->MB) kout->put8(kout->bK + ch, kv);   // the normalised k'': kscale goes into its partners
   }
+  });
   // ---- D1 = K P' on the tensor core ----
   tc_contract(c, c.K1, c.K2, c.tmem);
   if (light) {     // uniform over the CTA: the moments come from the forward pass
@@ -530,16 +554,16 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16);   // this warp's 32-lane quarter
   uint32_t ra[16];
   if (g0 < MP / 16) tmem_ld16_issue(trow + g0 * 16, ra);
-#pragma unroll(MC ? kTcChunkUnroll : 1)
-  for (int cc = g0; cc < MP / 16; cc += NG) {
+  for_chunks<MC, NG>(g0, MP / 16, [&](const int cc, auto rows_tag) {
+    constexpr int ROWS = decltype(rows_tag)::value;
     float a[16], kp[16];
-    tc_read_row16(c.K1, c.K2, t, cc, kp);
+    tc_read_row16<ROWS>(c.K1, c.K2, t, cc, kp);
     tmem_ld_wait(ra);
 #pragma unroll
     for (int e = 0; e < 16; ++e) a[e] = __uint_as_float(ra[e]);
     if (cc + NG < MP / 16) tmem_ld16_issue(trow + (cc + NG) * 16, ra);   // next chunk in flight during this one's math
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < ROWS; ++e) {
       const int m = cc * 16 + e;
       const float a2 = a[e] * a[e];
       float S[DOUTP];
@@ -557,7 +581,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
         for (int d = 0; d < D2; ++d) fv2[d] = fma2(pack2(S[2 * d], S[2 * d + 1]), aa, fv2[d]);
       }
     }
-  }
+  });
   q += qb;
   amax = fmaxf(amax, amaxb);
 #pragma unroll
@@ -651,8 +675,8 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   // ---- b'' = a' (S gv) 2^-e -> fp16 split rows of B ----
   uint32_t ra1[16];
   if (g0 < MP / 16) tmem_ld16_issue(trow1 + g0 * 16, ra1);
-#pragma unroll(MC ? kTcChunkUnroll : 1)
-  for (int cc = g0; cc < MP / 16; cc += NG) {
+  for_chunks<MC, NG>(g0, MP / 16, [&](const int cc, auto rows_tag) {
+    constexpr int ROWS = decltype(rows_tag)::value;
     float a[16];
     tmem_ld_wait(ra1);
 #pragma unroll
@@ -660,7 +684,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     if (cc + NG < MP / 16) tmem_ld16_issue(trow1 + (cc + NG) * 16, ra1);
     float bv[16], a2[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < ROWS; ++e) {
       const int m = cc * 16 + e;
       float S[DOUTP];
       ld_row<DOUTP>(c.Sm + m * DOUTP, S);
@@ -671,19 +695,20 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       a2[e] = a[e] * a[e];
       a[e] *= acoef;
     }
-    tmem_st16(trow1 + cc * 16, a);
-    float lo[8], hi[8];
+    tmem_st16(trow1 + cc * 16, a);       // (columns of padded rows are never read back)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { lo[e] = bv[e]; hi[e] = bv[8 + e]; }
-    tc_write_row8(c.B1, c.B2, t, 2 * cc, lo);
-    tc_write_row8(c.B1, c.B2, t, 2 * cc + 1, hi);
-    if (live) {
+    for (int hh = 0; hh < ROWS / 8; ++hh) {
+      float g8[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { lo[e] = a2[e]; hi[e] = a2[8 + e]; }
-      if (2 * cc < o.MB) o.put8(o.bA2 + 2 * cc, lo);
-      if (2 * cc + 1 < o.MB) o.put8(o.bA2 + 2 * cc + 1, hi);
+      for (int e = 0; e < 8; ++e) g8[e] = bv[8 * hh + e];
+      tc_write_row8(c.B1, c.B2, t, 2 * cc + hh, g8);
+      if (live && 2 * cc + hh < o.MB) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g8[e] = a2[8 * hh + e];
+        o.put8(o.bA2 + 2 * cc + hh, g8);
+      }
     }
-  }
+  });
   tmem_st_wait();
   tc_fence_before();
   uint4 kq[4];   // raw hi/lo segments of two row-blocks of k' (one 16-row chunk), fetched one chunk ahead
@@ -708,8 +733,8 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   for (int j = 0; j < N2; ++j) xs2[j] = 0ull;
 #pragma unroll
   for (int j = 0; j < N2b; ++j) xs2b[j] = 0ull;
-#pragma unroll(MC ? kTcChunkUnroll : 1)
-  for (int cc = g0; cc < MP / 16; cc += NG) {
+  for_chunks<MC, NG>(g0, MP / 16, [&](const int cc, auto rows_tag) {
+    constexpr int ROWS = decltype(rows_tag)::value;
     float pb[16], kp[16], bb[16];
     {
       uint32_t rp[16];
@@ -717,13 +742,13 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       // k'' of this chunk was fetched one iteration ahead; fetch the next chunk's now
       const uint4 c0 = kq[0], c1 = kq[1], c2 = kq[2], c3 = kq[3];
       if (cc + NG < MP / 16) o.get8_raw(o.bK + 2 * (cc + NG), live, kq);
-      tc_read_row16(c.B1, c.B2, t, cc, bb);
+      tc_read_row16<ROWS>(c.B1, c.B2, t, cc, bb);
       {
         float k0[8], k1[8];
         TcOut::unpack8(c0, c1, k0);
-        TcOut::unpack8(c2, c3, k1);
+        if (ROWS > 8) TcOut::unpack8(c2, c3, k1);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { kp[e] = k0[e]; kp[8 + e] = k1[e]; }
+        for (int e = 0; e < 8; ++e) { kp[e] = k0[e]; if (ROWS > 8) kp[8 + e] = k1[e]; }
       }
       tmem_ld_wait(rp);
 #pragma unroll
@@ -731,7 +756,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
     }
     float wv[16], abv[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < ROWS; ++e) {
       const int m = cc * 16 + e;
       float al[DOUTP];
       ld_row<DOUTP>(c.al + m * DOUTP, al);
@@ -767,17 +792,20 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       abv[e] = fmaf(c_k, kp[e], c_bb * bb[e]);  // kscale * a_bar (its partner operand holds k'')
     }
     if (live) {
-      float lo[8], hi[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { lo[e] = wv[e]; hi[e] = wv[8 + e]; }
-      if (2 * cc < o.MB) o.put8(o.bW + 2 * cc, lo);
-      if (2 * cc + 1 < o.MB) o.put8(o.bW + 2 * cc + 1, hi);
+      for (int hh = 0; hh < ROWS / 8; ++hh) {
+        if (2 * cc + hh < o.MB) {
+          float g8[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { lo[e] = abv[e]; hi[e] = abv[8 + e]; }
-      if (2 * cc < o.MB) o.put8(o.bAb + 2 * cc, lo);
-      if (2 * cc + 1 < o.MB) o.put8(o.bAb + 2 * cc + 1, hi);
+          for (int e = 0; e < 8; ++e) g8[e] = wv[8 * hh + e];
+          o.put8(o.bW + 2 * cc + hh, g8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g8[e] = abv[8 * hh + e];
+          o.put8(o.bAb + 2 * cc + hh, g8);
+        }
+      }
     }
-  }
+  });
   sw += swb;
 #pragma unroll
   for (int j = 0; j < N2b; ++j) if (kTwo) xs2[j] = add2(xs2[j], xs2b[j]);
