@@ -1083,13 +1083,16 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
   }
   const bool saved = ws.FVf != nullptr;      // (fmean, fvar, amax) of every step left by fw_forward_tc
+  // fetched one time step ahead for few state dims; for many (2 DX + 1 = 29 registers held across a whole evaluation
+  // at DX = 14) the kernel spills instead, and the values are loaded where they are used
+  constexpr bool kAhead = DX <= 8;
   float fnext[2 * DX + 1];
   auto load_saved = [&](int t) {
     const float *Fp = ws.FVf + ((size_t)t * (2 * DX + 1)) * np + nr;
 #pragma unroll
     for (int j = 0; j < 2 * DX + 1; ++j) fnext[j] = Fp[(size_t)j * np];
   };
-  if (saved) load_saved(win.t_hi);
+  if (saved && kAhead) load_saved(win.t_hi);
 #pragma unroll 1
   for (int t = win.t_hi; t >= win.t_lo; --t) {
     float x[DX], xin[DIN], xt[Ctx::DINP], fm[DX], fv[DX], yt[DX], amax, kscale;
@@ -1112,10 +1115,11 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     const float e = eps_f[(size_t)t * D.n_local + nr];
     const TcOut o = tc_out_at(mats, (size_t)(t - win.t_lo) * D.n_local + nr);
     if (saved) {
+      if (!kAhead) load_saved(t);
 #pragma unroll
       for (int j = 0; j < DX; ++j) { fm[j] = fnext[j]; fv[j] = fnext[DX + j]; }
       amax = fnext[2 * DX];
-      if (t > win.t_lo) load_saved(t - 1);
+      if (kAhead && t > win.t_lo) load_saved(t - 1);
     }
     gp_forward_tc<Ctx, DIN, DX>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale, saved);
     const bool do_cond = D.condition || (t < D.R - 1);
@@ -1225,6 +1229,7 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     for (int j = 0; j < DH; ++j) yv[j] = Yq[j * np];
   };
   const bool saved = ws.FVb != nullptr;      // (fmean, fvar, amax) of every step left by bm_forward_tc
+  constexpr bool kAhead = DX <= 8;           // as in fw_reverse_tc_kernel
   float fnext[2 * DH + 1];
   auto load_saved = [&](int t) {
     const float *Fp = ws.FVb + (((size_t)ch.run * D.T + t) * (2 * DH + 1)) * np + nr;
@@ -1233,7 +1238,7 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
   };
   load_hidden(ch.t_lo, hnext);
   load_ybar(ch.t_lo, ynext);
-  if (saved) load_saved(ch.t_lo);
+  if (saved && kAhead) load_saved(ch.t_lo);
 #pragma unroll 1
   for (int t = ch.t_lo; t <= ch.t_hi; ++t) {
     float hid[DH], ybar[DH], xin[DIN], xt[Ctx::DINP], fm[DH], fv[DH], amax, kscale;
@@ -1249,10 +1254,11 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
     const float e = eps_b[((size_t)ch.run * D.T + t) * D.n_local + nr];
     const TcOut o = tc_out_at(mats, ((size_t)ch.col0 + (t - ch.t_lo)) * D.n_local + nr);
     if (saved) {
+      if (!kAhead) load_saved(t);
 #pragma unroll
       for (int j = 0; j < DH; ++j) { fm[j] = fnext[j]; fv[j] = fnext[DH + j]; }
       amax = fnext[2 * DH];
-      if (t < ch.t_hi) load_saved(t + 1);
+      if (kAhead && t < ch.t_hi) load_saved(t + 1);
     }
     gp_forward_tc<Ctx, DIN, DH>(c, xin, xt, fm, fv, live ? &o : nullptr, amax, kscale, saved);
     const bool write = writer_run(t, D.R) == ch.run;
