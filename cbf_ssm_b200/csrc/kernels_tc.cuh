@@ -1076,16 +1076,16 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
 #pragma unroll
     for (int j = 0; j < DX; ++j) xb[j] = live ? ws.carry_f[j * np + nr] : 0.f;
   }
+  // fetched one time step ahead for few state dims; for many (2 DX + 1 = 29 registers held across a whole evaluation
+  // at DX = 14) the kernel spills instead, and the values are loaded where they are used
+  constexpr bool kAhead = DX <= 8;
   float xnext[DX];   // x_t of the coming iteration, fetched one step ahead (it heads the step's dependency chain)
-  {
+  if (kAhead) {
     const float *Xp = ws.X + ((size_t)win.t_hi * DX) * np + nr;
 #pragma unroll
     for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
   }
   const bool saved = ws.FVf != nullptr;      // (fmean, fvar, amax) of every step left by fw_forward_tc
-  // fetched one time step ahead for few state dims; for many (2 DX + 1 = 29 registers held across a whole evaluation
-  // at DX = 14) the kernel spills instead, and the values are loaded where they are used
-  constexpr bool kAhead = DX <= 8;
   float fnext[2 * DX + 1];
   auto load_saved = [&](int t) {
     const float *Fp = ws.FVf + ((size_t)t * (2 * DX + 1)) * np + nr;
@@ -1096,9 +1096,14 @@ __global__ void __launch_bounds__(NT * NG * kTcThreads, (NT == 1 && NG == 1) ? 2
 #pragma unroll 1
   for (int t = win.t_hi; t >= win.t_lo; --t) {
     float x[DX], xin[DIN], xt[Ctx::DINP], fm[DX], fv[DX], yt[DX], amax, kscale;
+    if (!kAhead) {
+      const float *Xp = ws.X + ((size_t)t * DX) * np + nr;
+#pragma unroll
+      for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
+    }
 #pragma unroll
     for (int j = 0; j < DX; ++j) { x[j] = xnext[j]; xin[j] = x[j]; }
-    if (t > win.t_lo) {
+    if (kAhead && t > win.t_lo) {
       const float *Xp = ws.X + ((size_t)(t - 1) * DX) * np + nr;
 #pragma unroll
       for (int j = 0; j < DX; ++j) xnext[j] = Xp[j * np];
