@@ -463,10 +463,11 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   }
   // packed FP32 (FADD2 / FFMA2 / FMUL2): pairs of input dims for delta, pairs of output dims for the sums
   constexpr int J2 = (DIN + 1) / 2, D2 = (DOUT + 1) / 2;
-  // Every sum over the inducing rows runs as two interleaved chains (even / odd rows): with two warps per
-  // scheduler a single 16-long dependent FMA chain per chunk leaves the issue slot idle for its latency.
-  // (only for few dims: at DIN = 21 / DOUT = 14 the second set of accumulators spills)
-  constexpr bool kTwo = DIN <= 8;
+  // In the latency variant every sum over the inducing rows runs as two interleaved chains (even / odd rows): with
+  // few warps a single 16-long dependent FMA chain per chunk leaves the issue slot idle for its latency.  The
+  // throughput kernels keep one chain (measured: the second set of accumulators costs 1.4 % of the step at the bench
+  // batch, and spills at DIN = 21 / DOUT = 14).
+  constexpr bool kTwo = NG > 1 && DIN <= 8;
   constexpr int D2b = kTwo ? D2 : 1;
   unsigned long long x2[J2], fm2[D2], fv2[D2], fm2b[D2b], fv2b[D2b];
 #pragma unroll
@@ -721,7 +722,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
   const float kfac = sig2 * kscale;             // k_m = kfac * k''_m
   const float c_pb = 2.f * pbs * kfac, c_bb = 2.f * bs * kscale, c_k = -Gs * kfac * kscale;
   constexpr int J2 = (DIN + 1) / 2, N2 = (NEED + 1) / 2;
-  constexpr bool kTwo = DIN <= 8;   // two chains (even / odd rows) only where the second set of accumulators fits the registers
+  constexpr bool kTwo = NG > 1 && DIN <= 8;   // two chains (even / odd rows): latency variant only, as in gp_forward_tc
   constexpr int N2b = kTwo ? N2 : 1, J2b = kTwo ? J2 : 1;
   unsigned long long x2[J2], xs2[N2], L2[J2], xs2b[N2b], L2b[J2b];   // packed over input-dim pairs (2j, 2j+1)
   float swb = 0.f;
