@@ -66,6 +66,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// the same with the A operand in TMEM (lane = row, 8 columns = 16 packed K elements per instruction)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -121,6 +129,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 4 consecutive 32-bit columns (8 packed 16-bit operand elements) of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&w)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait4(uint32_t (&a)[4], uint32_t (&b)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   tmem_ld16_issue(taddr, r);
@@ -158,8 +183,16 @@ struct TcCtx {
   static constexpr int XV = 1 + (2 * DOUT + 2) + DIN;   // exchange values per (group, particle): d2min | q, amax, fm, fv | x_bar
   static constexpr int MC = MC_;     // compile-time M (0: runtime) -- lets the M loops unroll and drop their guards
   static constexpr int DINP = (DIN + 3) / 4 * 4, DOUTP = (DOUT + 3) / 4 * 4;
-  static constexpr uint32_t kTmemAlloc = NT <= 1 ? 128u : NT == 2 ? 256u : 512u;   // allocations are powers of two
-  static constexpr uint32_t TMEM_COLS = 128u;   // one fp32 accumulator (MP <= 128 columns) per tile; the reverse pass reuses it
+  // The A operands of the contractions (k'' and, in the reverse pass, b'': two fp16 terms each) live in TMEM next to
+  // the accumulator when the tile's 256 columns fit: each thread writes its own particle's row with tcgen05.st (lane =
+  // row; column c holds the K elements 2c, 2c+1, low half first -- tools/microbench/tmem_a.cu) and tcgen05.mma reads
+  // them from there.  That takes the operand stores, their read-backs and the tensor core's A reads off the
+  // shared-memory data path, the busiest unit of these kernels.  Three-tile CTAs (3 x 256 columns do not exist) keep
+  // the operands in shared memory.
+  static constexpr bool kATmem = NT <= 2;
+  static constexpr uint32_t TMEM_COLS = kATmem ? 256u : 128u;   // accumulator (MP <= 128 columns) [+ 2 x MP/2 operand columns]
+  static constexpr uint32_t kAOff = 128u;                        // first operand column of a tile
+  static constexpr uint32_t kTmemAlloc = NT * TMEM_COLS <= 256u ? 256u : 512u;   // allocations are powers of two
   __half *P1, *P2, *K1, *K2, *B1, *B2;
   const float *Zt, *al, *Sm, *il;
   float *xch;           // (NG > 1) [NG][XV][128] partial sums between the groups of a particle
@@ -277,6 +310,12 @@ struct TcCtx {
     tc_fence_after();
     tmem_base = *tmemp;
     tmem = tmem_base + (uint32_t)tile * TMEM_COLS;
+    if constexpr (kATmem) {   // operand columns start as zeros (TMEM comes uninitialised; a padding group is never written)
+      const uint32_t z[4] = {0u, 0u, 0u, 0u};
+      const uint32_t trow = tmem + ((uint32_t)(tl_ & ~31) << 16) + kAOff;
+      for (int c4 = 0; c4 < MP / 4; ++c4) tmem_st4(trow + c4 * 4, z);
+      tmem_st_wait();
+    }
     return base;
   }
 
@@ -292,6 +331,7 @@ struct TcCtx {
 // and the mbarrier wait).  a1/a2: fp16 split A operands written by the threads just before.
 template <class Ctx>
 __device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __half *a2p, uint32_t tmem_d, uint32_t acc0 = 0) {
+  if constexpr (Ctx::kATmem) tmem_st_wait();   // this thread's operand rows (and scaled accumulator row) are in TMEM
   async_proxy_fence();
   tc_fence_before();
   if (Ctx::NT == 1) __syncthreads(); else tile_sync(c.tile_id());
@@ -299,12 +339,16 @@ __device__ __forceinline__ void tc_contract(Ctx &c, const __half *a1p, const __h
     tc_fence_after();
     const uint32_t lboA = kTcThreads * 16, lboB = c.MP * 16;
     const uint32_t a1 = smem_u32(a1p), a2 = smem_u32(a2p), b1 = smem_u32(c.P1), b2 = smem_u32(c.P2);
+    const uint32_t ta1 = c.tmem + Ctx::kAOff, ta2 = ta1 + c.MP / 2;   // (kATmem) operand terms: MP / 2 columns each
     const int ks = c.MP / 16;
     uint32_t acc = acc0;   // 1: add to what the threads stored in the accumulator columns
     for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t ab = (pass == 1) ? a2 : a1, bb = (pass == 2) ? b2 : b1;
+      const uint32_t ab = (pass == 1) ? a2 : a1, bb = (pass == 2) ? b2 : b1, tab = (pass == 1) ? ta2 : ta1;
       for (int k = 0; k < ks; ++k) {
-        umma_f16(tmem_d, umma_desc(ab + k * 2 * lboA, lboA, 128), umma_desc(bb + k * 2 * lboB, lboB, 128), c.idesc, acc);
+        if constexpr (Ctx::kATmem)
+          umma_f16_ts(tmem_d, tab + k * 8, umma_desc(bb + k * 2 * lboB, lboB, 128), c.idesc, acc);   // 8 columns = 16 K elements
+        else
+          umma_f16(tmem_d, umma_desc(ab + k * 2 * lboA, lboA, 128), umma_desc(bb + k * 2 * lboB, lboB, 128), c.idesc, acc);
         acc = 1;
       }
     }
@@ -365,6 +409,52 @@ __device__ __forceinline__ void tc_write_row8(__half *b1, __half *b2, int row, i
   const size_t off = (size_t)ch * (kTcThreads * 8) + row * 8;
   *reinterpret_cast<uint4 *>(b1 + off) = v1;
   *reinterpret_cast<uint4 *>(b2 + off) = v2;
+}
+
+// Operand rows of the tile's A operand pair, in TMEM (Ctx::kATmem) or in the shared-memory buffers b1 / b2.
+template <class Ctx>
+__device__ __forceinline__ void tc_put_row8(const Ctx &c, __half *b1, __half *b2, int row, int ch, const float (&v)[8]) {
+  if constexpr (Ctx::kATmem) {
+    uint32_t w1[4], w2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 h1 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      const float2 f1 = __half22float2(h1);
+      const __half2 h2 = __floats2half2_rn(v[2 * e] - f1.x, v[2 * e + 1] - f1.y);
+      w1[e] = *reinterpret_cast<const uint32_t *>(&h1);
+      w2[e] = *reinterpret_cast<const uint32_t *>(&h2);
+    }
+    const uint32_t trow = c.tmem + ((uint32_t)(row & ~31) << 16) + Ctx::kAOff + ch * 4;
+    tmem_st4(trow, w1);
+    tmem_st4(trow + c.MP / 2, w2);
+  } else {
+    tc_write_row8(b1, b2, row, ch, v);
+  }
+}
+template <int ROWS, class Ctx>
+__device__ __forceinline__ void tc_get_row16(const Ctx &c, const __half *b1, const __half *b2, int row, int cc, float (&v)[16]) {
+  if constexpr (Ctx::kATmem) {
+    const uint32_t trow = c.tmem + ((uint32_t)(row & ~31) << 16) + Ctx::kAOff + cc * 8;
+    uint32_t w1[ROWS / 8][4], w2[ROWS / 8][4];
+#pragma unroll
+    for (int hch = 0; hch < ROWS / 8; ++hch) {
+      tmem_ld4_issue(trow + hch * 4, w1[hch]);
+      tmem_ld4_issue(trow + c.MP / 2 + hch * 4, w2[hch]);
+    }
+#pragma unroll
+    for (int hch = 0; hch < ROWS / 8; ++hch) {
+      tmem_ld_wait4(w1[hch], w2[hch]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w1[hch][e]));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w2[hch][e]));
+        v[hch * 8 + 2 * e] = f1.x + f2.x;
+        v[hch * 8 + 2 * e + 1] = f1.y + f2.y;
+      }
+    }
+  } else {
+    tc_read_row16<ROWS>(b1, b2, row, cc, v);
+  }
 }
 
 // x = hi + lo with two bfloat16 terms (round-to-nearest each): 8 values -> two 16-byte segments.
@@ -539,7 +629,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       }
       kv[e] = kp;
     }
-    tc_write_row8(c.K1, c.K2, t, ch, kv);
+    tc_put_row8(c, c.K1, c.K2, t, ch, kv);
     if (kout && ch < kout->MB) kout->put8(kout->bK + ch, kv);   // the normalised k'': kscale goes into its partners
   }
   });
@@ -558,7 +648,7 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
   for_chunks<MC, NG>(g0, MP / 16, [&](const int cc, auto rows_tag) {
     constexpr int ROWS = decltype(rows_tag)::value;
     float a[16], kp[16];
-    tc_read_row16<ROWS>(c.K1, c.K2, t, cc, kp);
+    tc_get_row16<ROWS>(c, c.K1, c.K2, t, cc, kp);
     tmem_ld_wait(ra);
 #pragma unroll
     for (int e = 0; e < 16; ++e) a[e] = __uint_as_float(ra[e]);
@@ -702,7 +792,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       float g8[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) g8[e] = bv[8 * hh + e];
-      tc_write_row8(c.B1, c.B2, t, 2 * cc + hh, g8);
+      tc_put_row8(c, c.B1, c.B2, t, 2 * cc + hh, g8);
       if (live && 2 * cc + hh < o.MB) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) g8[e] = a2[8 * hh + e];
@@ -743,7 +833,7 @@ __device__ __forceinline__ void gp_reverse_tc(Ctx &c, const float (&xt)[(DIN + 3
       // k'' of this chunk was fetched one iteration ahead; fetch the next chunk's now
       const uint4 c0 = kq[0], c1 = kq[1], c2 = kq[2], c3 = kq[3];
       if (cc + NG < MP / 16) o.get8_raw(o.bK + 2 * (cc + NG), live, kq);
-      tc_read_row16<ROWS>(c.B1, c.B2, t, cc, bb);
+      tc_get_row16<ROWS>(c, c.B1, c.B2, t, cc, bb);
       {
         float k0[8], k1[8];
         TcOut::unpack8(c0, c1, k0);
