@@ -207,9 +207,11 @@ struct TcCtx {
   float sig2, pscale;   // P = pscale * P'
   float smax[DOUT];     // max_m S_md (bound used to scale b in the reverse pass)
 
+  // shared-memory operand buffers (k'' / b'' rows and the parked squared distances): none when they live in TMEM
+  __host__ __device__ static size_t kbuf_bytes(int MP) { return kATmem ? 0 : (size_t)NT * 2 * kTcThreads * MP * 2; }
   static size_t bytes(int M) {
     const int MP = round_up(M, 16);
-    return (size_t)2 * MP * MP * 2 + (size_t)NT * 2 * kTcThreads * MP * 2 +
+    return (size_t)2 * MP * MP * 2 + kbuf_bytes(MP) +
            sizeof(float) * ((size_t)MP * (DINP + 2 * DOUTP) + DINP + 4) + 64 +
            (NG > 1 ? sizeof(float) * (size_t)NG * XV * kTcThreads : 0);
   }
@@ -221,16 +223,16 @@ struct TcCtx {
     P2 = reinterpret_cast<__half *>(base); base += (size_t)MP * MP * 2;
     tile_ = threadIdx.x / kTcThreads; tl_ = threadIdx.x % kTcThreads;
     const int tile = tile_id();     // 0 in the M-split variant: all groups share one tile's buffers
-    K1 = reinterpret_cast<__half *>(base) + (size_t)(2 * tile) * kTcThreads * MP;
-    K2 = K1 + (size_t)kTcThreads * MP;
-    base += (size_t)NT * 2 * kTcThreads * MP * 2;
+    K1 = reinterpret_cast<__half *>(base) + (kATmem ? 0 : (size_t)(2 * tile) * kTcThreads * MP);   // (unused with kATmem)
+    K2 = K1 + (kATmem ? 0 : (size_t)kTcThreads * MP);
+    base += kbuf_bytes(MP);
     // The reverse pass reuses the K operand buffers for b (k is re-read from the float32 operand
     // matrix it was just written to, an L2 hit), which keeps the CTA at ~114 KB: two CTAs per SM.
     B1 = K1; B2 = K2;
     {   // every row group the kernels visit is rewritten each evaluation; a padding group they skip (for_chunks) must
         // read as zeros in the contractions, so the buffers start zeroed
-      uint4 *kz = reinterpret_cast<uint4 *>(base - (size_t)NT * 2 * kTcThreads * MP * 2);
-      const int n16 = (int)((size_t)NT * 2 * kTcThreads * MP * 2 / 16);
+      uint4 *kz = reinterpret_cast<uint4 *>(base - kbuf_bytes(MP));
+      const int n16 = (int)(kbuf_bytes(MP) / 16);
       for (int i = threadIdx.x; i < n16; i += blockDim.x) kz[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     // The tables have MP rows (Zt holds -Z/ell so that delta is one packed add): rows >= M hold Z/ell = 1e18 (squared distance ~1e37, so k'' underflows to an
@@ -592,11 +594,20 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
       if (kTwo && (e & 1)) d2minb = fminf(d2minb, d2); else d2min = fminf(d2min, d2);
       dv[e] = d2;
     }
-    const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
-    *reinterpret_cast<float4 *>(c.K1 + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
-    *reinterpret_cast<float4 *>(c.K2 + off) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+    if constexpr (Ctx::kATmem) {   // parked in the (idle until the contraction) accumulator columns of the own lane
+      const uint32_t w0[4] = {__float_as_uint(dv[0]), __float_as_uint(dv[1]), __float_as_uint(dv[2]), __float_as_uint(dv[3])};
+      const uint32_t w1[4] = {__float_as_uint(dv[4]), __float_as_uint(dv[5]), __float_as_uint(dv[6]), __float_as_uint(dv[7])};
+      const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16) + ch * 8;
+      tmem_st4(trow, w0);
+      tmem_st4(trow + 4, w1);
+    } else {
+      const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
+      *reinterpret_cast<float4 *>(c.K1 + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+      *reinterpret_cast<float4 *>(c.K2 + off) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+    }
   }
   });
+  if constexpr (Ctx::kATmem) tmem_st_wait();
   d2min = fminf(d2min, d2minb);
   if (NG > 1) {   // the particle's minimum over all groups
     *c.xslot(g0, 0) = d2min;
@@ -609,9 +620,20 @@ __device__ __forceinline__ void gp_forward_tc(Ctx &c, const float (&xin)[DIN], f
 #pragma unroll
   for (int hh = 0; hh < decltype(rows_tag)::value / 8; ++hh) {
     const int ch = 2 * cc + hh;
-    const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
-    const float4 da = *reinterpret_cast<const float4 *>(c.K1 + off), db = *reinterpret_cast<const float4 *>(c.K2 + off);
-    const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+    float dv[8];
+    if constexpr (Ctx::kATmem) {
+      uint32_t w0[4], w1[4];
+      const uint32_t trow = c.tmem + ((uint32_t)(t & ~31) << 16) + ch * 8;
+      tmem_ld4_issue(trow, w0);
+      tmem_ld4_issue(trow + 4, w1);
+      tmem_ld_wait4(w0, w1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { dv[e] = __uint_as_float(w0[e]); dv[4 + e] = __uint_as_float(w1[e]); }
+    } else {
+      const size_t off = (size_t)ch * (kTcThreads * 8) + t * 8;
+      const float4 da = *reinterpret_cast<const float4 *>(c.K1 + off), db = *reinterpret_cast<const float4 *>(c.K2 + off);
+      dv[0] = da.x; dv[1] = da.y; dv[2] = da.z; dv[3] = da.w; dv[4] = db.x; dv[5] = db.y; dv[6] = db.z; dv[7] = db.w;
+    }
     float kv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
