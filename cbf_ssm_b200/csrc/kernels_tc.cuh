@@ -3,15 +3,19 @@
 // For a CTA tile of 128 particles the M x M contraction a = P k of every time step is a real
 // GEMM, D[128 x MP] = K[128 x MP] . P[MP x MP], and runs on the 5th-generation tensor cores:
 //   * one thread = one particle = one TMEM lane; each step the thread evaluates its kernel vector
-//     k' = k / sigma^2 in (0,1] (SIMT: one FFMA chain + one MUFU.EX2 per inducing point), splits it
-//     into two fp16 terms k' = h1 + h2 (22 significant bits together) and stores both as rows of
-//     the K-major A operands K1, K2 in shared memory (canonical no-swizzle core-matrix layout,
-//     16-byte chunk c of row r at c*2048 + r*16: conflict-free 128-bit stores);
-//   * P' = P / 2^e (|P'| <= 1024) is split the same way once per launch into the B operands P1, P2;
-//   * one elected thread issues 3 x MP/16 tcgen05.mma.kind::f16 (K1 P1 + K2 P1 + K1 P2, fp32
+//     k'' = k / (sigma^2 max_m k) in (0,1] (SIMT: one packed-FMA chain + one MUFU.EX2 per inducing point; the squared
+//     distances wait in the thread's own, still idle accumulator columns while their minimum is found), splits it
+//     into two fp16 terms k'' = h1 + h2 (22 significant bits together) and writes both as its row of the A operand
+//     pair -- in TMEM, next to the accumulator (tcgen05.st; lane = row, one 32-bit column = two K elements:
+//     TcCtx::kATmem, tools/microbench/tmem_a.cu).  Only three-tile CTAs, whose 3 x 256 columns do not exist, keep
+//     the operands in shared memory (K1, K2: canonical no-swizzle core-matrix layout, 16-byte chunk c of row r at
+//     c*2048 + r*16: conflict-free 128-bit stores);
+//   * P' = P / 2^e (|P'| <= 1024) is split the same way once per launch into the B operands P1, P2 (shared memory);
+//   * one elected thread issues 3 x MP/16 tcgen05.mma.kind::f16 (K1 P1 + K2 P1 + K1 P2, A from TMEM, fp32
 //     accumulation in TMEM; the dropped h2*h2 term is < 2^-22 relative) and commits to an mbarrier;
 //   * every thread reads its accumulator row back with tcgen05.ld (16 columns at a time) and
-//     forms k.a and sum_m a_m^2 S_md in fp32 (SIMT), re-reading its own k' row from K1/K2.
+//     forms k.a and sum_m a_m^2 S_md in fp32 (SIMT), re-reading its own k'' row from the operand columns.
+// A CTA is 57 KB of shared memory (P1, P2, the small GP tables) and 256 TMEM columns: two CTAs per SM.
 // The O(M.D) work stays on the SIMT pipes; only the 2 M^2 FLOPs per evaluation move to the tensor
 // pipe.
 //
