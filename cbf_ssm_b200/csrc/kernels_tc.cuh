@@ -230,8 +230,8 @@ struct TcCtx {
     K1 = reinterpret_cast<__half *>(base) + (kATmem ? 0 : (size_t)(2 * tile) * kTcThreads * MP);   // (unused with kATmem)
     K2 = K1 + (kATmem ? 0 : (size_t)kTcThreads * MP);
     base += kbuf_bytes(MP);
-    // The reverse pass reuses the K operand buffers for b (k is re-read from the float32 operand
-    // matrix it was just written to, an L2 hit), which keeps the CTA at ~114 KB: two CTAs per SM.
+    // The reverse pass reuses the K operand rows for b (k is re-read from the operand tile it was just written to,
+    // an L2 hit), so one operand pair per tile suffices.
     B1 = K1; B2 = K2;
     {   // every row group the kernels visit is rewritten each evaluation; a padding group they skip (for_chunks) must
         // read as zeros in the contractions, so the buffers start zeroed
