@@ -1456,16 +1456,12 @@ struct LaunchTc {
     return ctas <= sm_count();
   }
 
-  // Three-tile CTAs when the estimated makespan is shorter: a wave of them (3 tiles per SM) takes kTriSlow times a wave
-  // of one-tile CTAs (2 tiles per SM; measured 1.48 at M = 100), and a launch takes whole waves of either kind.
-  static constexpr float kTriSlow = 1.48f;
-  static bool want_tri(int tiles, int nchain) {
-    const char *e = getenv("CBFSSM_B200_TC_TILES");      // 1: never, 3: always (tests, measurement), unset: by launch size
-    if (e != nullptr && *e) return atoi(e) == 3;
-    const int sms = sm_count();
-    const float w1 = (float)ceil_div(tiles * nchain, 2 * sms);
-    const float w3 = kTriSlow * (float)ceil_div(ceil_div(tiles, 3) * nchain, sms);
-    return w3 < w1;
+  // Three-tile CTAs (12 warps per SM, operands in shared memory) were worth up to 4 % where they filled whole waves
+  // better than one-tile CTAs; since the one-tile kernels keep their operands in TMEM they are as fast or faster at
+  // every batch measured, so the variant is only taken on request (tests, measurements).
+  static bool want_tri(int, int) {
+    const char *e = getenv("CBFSSM_B200_TC_TILES");      // 3: three-tile CTAs where they fit; anything else: never
+    return e != nullptr && *e && atoi(e) == 3;
   }
 
   // Launch `k1` (one particle tile per CTA), or `ks` (one tile, kSplitG threads per particle) when the launch is
