@@ -167,11 +167,10 @@ __device__ __forceinline__ void split_h(float x, __half &h1, __half &h2) {
   h2 = __float2half_rn(x - __half2float(h1));
 }
 
-// Shared-memory state of one CTA: operands, resident small GP tables, barrier, TMEM base.
-// NT particle tiles per CTA (NT x 128 threads): each tile has its own operand buffers, TMEM columns, mbarrier
+// Shared-memory / TMEM state of one CTA: the B operand pair P1/P2, resident small GP tables, barrier, TMEM base.
+// NT particle tiles per CTA (NT x 128 threads): each tile has its own operand rows, TMEM columns, mbarrier
 // and named barrier and runs independently; the tiles share P1/P2 and the small tables.  NT = 2 is used
-// where one tile's CTA is too large for two CTAs per SM (D >= 8 at M = 100: 11-22 KB of tables), which
-// restores 8 warps per SM.
+// where one tile's CTA is too large for two CTAs per SM (large tables at M = 128), which restores 8 warps per SM.
 //
 // NG > 1 (latency variant, NT = 1 only): NG x 128 threads work on ONE particle tile, thread (g, lane) handling the
 // 16-row chunks cc = g, g + NG, ... of particle `lane`'s M-vectors (warps w and w + 4 read the same TMEM lane
@@ -1424,14 +1423,15 @@ struct LaunchTc {
   static constexpr int DH = DX - DY, DIN = DX + DU;
   // dims with a compile-time M = 100 instantiation (run/template.py, SpringNonlinear, Sarcos shapes)
   static constexpr bool kHas100 = (DX == 4 && (DU == 1 || DU == 2)) || DX == 14;
-  // dims whose tables can push a one-tile CTA past two CTAs per SM: the two-tile kernels are compiled too
+  // dims whose tables can push a one-tile CTA past two CTAs per SM (dx >= 8 at M = 128: 64 KB of P terms + 29 KB of
+  // tables): the two-tile kernels are compiled too, pick() takes them when the occupancy query says one CTA per SM
   static constexpr bool kDual = DX >= 8;
   // dims with the latency variant (kSplitG threads per particle, TcCtx NG): used when a launch has fewer CTAs than
   // the GPU has SMs, i.e. when the serial chain of a time step, not throughput, sets the kernel's duration
   static constexpr bool kSplit = DX <= 4;
   static constexpr int kSplitG = 2;
-  // small dims at M <= 112: three tiles sharing P fit one SM's shared memory (12 warps per SM instead of the 8 of two
-  // one-tile CTAs); used when the launch fills whole waves of them better (want_tri)
+  // small dims at M <= 112: three tiles sharing P fit one SM's shared memory with shared-memory operands (12 warps per
+  // SM instead of the 8 of two one-tile CTAs); taken on request only (want_tri)
   static constexpr bool kTri = !kDual && DX <= 4;
   static constexpr int kMulti = kDual ? 2 : (kTri ? 3 : 1);
   static constexpr size_t kMaxDyn = 227 * 1024;
